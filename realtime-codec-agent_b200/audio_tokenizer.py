@@ -1,0 +1,225 @@
+"""Drop-in ``AudioTokenizer`` for the B200 engine.
+
+Public surface, argument meaning, return shapes and quirks are those of
+/root/reference/realtime_codec_agent/audio_tokenizer.py (class at :10, ctor :11-42,
+tokenize_audio :67-103, detokenize_audio :105-149, get_codec_embeddings :151-159,
+_drop_hanging_channel_codes :161-168, _encode_silence :170-179, _compute_framerate :181-187,
+_prep_audio_for_tokenization :203-215).  What differs is what runs underneath:
+
+* ``codec_model="MagiCodec-50Hz-Base"`` (or a checkpoint path) builds a ``B200Generator``
+  (hand-written sm_100a kernels behind the C-ABI in include/magicodec_b200.h); there is no
+  CPU fallback — constructing it without a B200 and the built extension raises.
+* with a ``B200Generator`` all channels go through ONE batched engine call per
+  tokenize/detokenize (the reference loops batch-1 per channel, :83-86 and :136-139), only
+  the frames/samples the caller keeps are computed past the last attention layer and copied
+  back (:99-101, :141-144), and the projected codebook is cached (the reference re-projects
+  131 072 rows on every decode, :198).
+* any other duck-typed model object (``pad_audio/encoder/quantizer/decoder``) is driven
+  through exactly the calls the reference makes, so host-side behaviour can be compared
+  against the reference wrapper with the same model on either side.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from .codec_chars import UNICODE_OFFSET_LARGE, chars_to_codes, codes_to_chars
+
+AudioLike = Union[Tuple[int, np.ndarray], np.ndarray]
+
+
+def load_magicodec_model(name_or_path: str, device: torch.device):
+    """Counterpart of codec_bpe.tools.codec_utils.load_magicodec_model (audio_tokenizer.py:8,27).
+
+    Returns ``(model, None, None)`` like upstream's 3-tuple.  Resolution order: an existing
+    checkpoint file path; ``$MAGICODEC_B200_CHECKPOINT``; else seeded random-init weights of the
+    default spec (no checkpoint is reachable offline — BASELINE.json prescribes random init).
+    """
+    import os
+
+    from .generator import B200Generator
+    from .spec import DEFAULT_SPEC
+    from .weights import init_random_weights, load_checkpoint
+
+    path = name_or_path if os.path.isfile(name_or_path) else os.environ.get("MAGICODEC_B200_CHECKPOINT")
+    if path:
+        spec, weights = load_checkpoint(path)
+    else:
+        spec, weights = DEFAULT_SPEC, init_random_weights(DEFAULT_SPEC, seed=0)
+    return B200Generator(spec, weights, device=device), None, None
+
+
+class AudioTokenizer:
+    def __init__(
+        self,
+        codec_model: Union[str, Any] = "MagiCodec-50Hz-Base",
+        num_channels: int = 1,
+        context_secs: float = 2.0,
+        unicode_offset: int = UNICODE_OFFSET_LARGE,
+        device: Optional[Union[str, torch.device]] = None,
+    ):
+        if device is None:
+            device = "cuda" if torch.cuda.is_available() else "cpu"
+        self.device = torch.device(device)
+        self.autocast_bfloat16 = self.device.type == "cuda" and torch.cuda.is_bf16_supported()
+
+        if isinstance(codec_model, str):
+            codec_model = load_magicodec_model(codec_model, self.device)[0]
+        self.codec_model = codec_model.eval().to(self.device)
+        self._native = bool(getattr(self.codec_model, "is_b200_native", False))
+
+        self.num_channels = num_channels
+        self.num_codebooks = 1
+        self.codebook_size = self.codec_model.codebook_size
+        self.context_secs = context_secs
+        self.unicode_offset = unicode_offset
+        self.sampling_rate = self.codec_model.sample_rate
+        self.framerate = self._compute_framerate()
+        self.context_samples = int(self.context_secs * self.sampling_rate)
+        self.context_frames = int(self.context_secs * self.framerate * self.num_channels)
+        self.reset_context()
+
+    # ------------------------------------------------------------------ state
+    def reset_context(self):
+        self.tokenize_context = np.zeros((self.num_channels, 0), dtype=np.float32)
+        self.detokenize_context = ""
+
+    def get_audio_codes_str_secs(self, audio_codes_str: str) -> float:
+        return len(audio_codes_str) / (self.framerate * self.num_channels)
+
+    # ----------------------------------------------------------------- encode
+    def chunked_tokenize_audio(self, audio: AudioLike, chunk_size_secs: float) -> str:
+        sr, wav = (self.sampling_rate, audio) if isinstance(audio, np.ndarray) else audio
+        step = int(chunk_size_secs * sr)
+        total = wav.shape[-1]
+        return "".join(self.tokenize_audio((sr, wav[..., s:s + step])) for s in range(0, total, step))
+
+    @torch.inference_mode()
+    def tokenize_audio(self, audio: AudioLike) -> str:
+        new = self._prep_audio_for_tokenization(audio)
+        n_new = new.shape[-1]
+        C = self.num_channels
+        joined = np.concatenate((self.tokenize_context, new.reshape(C, -1)), axis=-1)
+        keep = max(n_new, self.context_samples)
+        self.tokenize_context = joined[..., -keep:]          # [-0:] keeps everything, as upstream
+
+        # chars the caller keeps: int(secs*framerate*C); a zero count slices [-0:] == whole string
+        n_chars = int(n_new / self.sampling_rate * self.framerate * C)
+
+        if self._native:
+            window = torch.from_numpy(np.ascontiguousarray(self.tokenize_context)).to(self.device, non_blocking=True)
+            frames_needed = -(-n_chars // C) if n_chars > 0 else 0          # 0 -> all frames
+            codes = self.codec_model.encode(window, keep_last_frames=frames_needed)  # [C,Fk] int64
+            per_channel = codes.cpu().numpy()[:, None, :]                   # [C,1,Fk]
+        else:
+            window = torch.tensor(self.tokenize_context).to(self.device)
+            with self._autocast():
+                per_channel = torch.cat([self._magicodec_encode(ch[None]) for ch in window], dim=0)
+            per_channel = per_channel.cpu().numpy()
+
+        text = self._interleave_chars(per_channel)
+        return text[-n_chars:]
+
+    def _interleave_chars(self, codes_c1f: np.ndarray) -> str:
+        """[C,1,F] codes -> 'c0[0] c1[0] c0[1] c1[1] ...' (audio_tokenizer.py:89-96)."""
+        C = codes_c1f.shape[0]
+        if C == 1:
+            return codes_to_chars(codes_c1f[0], self.codebook_size, unicode_offset=self.unicode_offset)
+        # same offset on every channel: channels are not codebooks
+        frame_major = np.ascontiguousarray(codes_c1f[:, 0, :].T).reshape(1, -1)
+        return codes_to_chars(frame_major, self.codebook_size, unicode_offset=self.unicode_offset)
+
+    # ----------------------------------------------------------------- decode
+    @torch.inference_mode()
+    def detokenize_audio(self, audio_codes_str: str, preroll_samples: int = 0):
+        audio_codes_str, end_hanging = self._drop_hanging_channel_codes(audio_codes_str)
+        C = self.num_channels
+        self.detokenize_context += audio_codes_str
+        keep = max(len(audio_codes_str), self.context_frames)
+        self.detokenize_context = self.detokenize_context[-keep:]
+
+        flat = chars_to_codes(self.detokenize_context, 1, self.codebook_size, unicode_offset=self.unicode_offset)[0]
+        codes = np.ascontiguousarray(flat.reshape(-1, C).T)                  # [C,F] de-interleave (:116)
+
+        want = int(self.get_audio_codes_str_secs(audio_codes_str) * self.sampling_rate) + preroll_samples
+
+        if self._native:
+            dev_codes = torch.from_numpy(codes).to(self.device, non_blocking=True)
+            wav = self.codec_model.decode(dev_codes, keep_last_samples=want)  # [C,Tk] fp32
+            wav = wav[None]                                                   # [1,C,Tk]
+        else:
+            dev_codes = torch.from_numpy(codes)[:, None, :].to(self.device)  # [C,1,F]
+            with self._autocast():
+                wav = torch.cat([self._magicodec_decode(ch[None]) for ch in dev_codes], dim=1)
+            wav = wav[..., -want:]                                            # [-0:] == everything
+
+        preroll_left = max(0, preroll_samples - want + wav.shape[-1])
+        out = wav[0, 0] if C == 1 else wav[0]
+        return (self.sampling_rate, out.cpu().numpy()), end_hanging, preroll_left
+
+    # ---------------------------------------------------------- codec details
+    @torch.inference_mode()
+    def get_codec_embeddings(self) -> torch.Tensor:
+        q = self.codec_model.quantizer
+        with self._autocast():
+            return q.codebook_proj(q.codebook.weight)
+
+    def _drop_hanging_channel_codes(self, audio_str: str) -> Tuple[str, str]:
+        extra = len(audio_str) % self.num_channels
+        if extra == 0:
+            return audio_str, ""
+        trimmed = audio_str[:-extra]
+        # upstream returns the tail of the ALREADY trimmed string (:164-165); kept bug-compatible
+        return trimmed, trimmed[-extra:]
+
+    @torch.inference_mode()
+    def _encode_silence(self, secs: float) -> torch.Tensor:
+        silence = torch.zeros(int(secs * self.sampling_rate), device=self.device)
+        with self._autocast():
+            return self._magicodec_encode(silence[None])
+
+    def _compute_framerate(self) -> float:
+        probe_secs = 10.0
+        frames = self._encode_silence(probe_secs).shape[-1]
+        samples_per_frame = math.ceil(int(probe_secs * self.sampling_rate) / frames)
+        return self.sampling_rate / samples_per_frame
+
+    def _magicodec_encode(self, x: torch.Tensor) -> torch.Tensor:
+        m = self.codec_model
+        if self._native:
+            return m.encode(x)[:, None, :]
+        z_e = m.encoder(m.pad_audio(x))
+        return m.quantizer.inference(z_e)[1].unsqueeze(1)
+
+    def _magicodec_decode(self, codes: torch.Tensor) -> torch.Tensor:
+        m = self.codec_model
+        codes = codes.squeeze(1)
+        if self._native:
+            return m.decode(codes)[:, None, :]
+        table = m.quantizer.codebook_proj(m.quantizer.codebook.weight)
+        return m.decoder(torch.nn.functional.embedding(codes, table)).float()
+
+    def _prep_audio_for_tokenization(self, audio: AudioLike) -> np.ndarray:
+        sr, wav = (self.sampling_rate, audio) if isinstance(audio, np.ndarray) else audio
+        if wav.dtype == np.int16:
+            wav = wav.astype("float32") / 32768.0
+        if self.num_channels == 1 and wav.ndim > 1:
+            wav = np.mean(wav, axis=0)                       # librosa.to_mono
+        if sr != self.sampling_rate:
+            wav = _resample(wav, sr, self.sampling_rate)
+        return wav
+
+    def _autocast(self):
+        return torch.autocast(device_type="cuda", dtype=torch.bfloat16, enabled=self.autocast_bfloat16)
+
+
+def _resample(wav: np.ndarray, orig_sr: int, target_sr: int) -> np.ndarray:
+    """Polyphase resampler standing in for ``librosa.resample`` (audio_tokenizer.py:214; librosa's
+    default soxr kernel is not available offline, so sample values differ in the last bits)."""
+    from scipy.signal import resample_poly
+
+    g = math.gcd(int(orig_sr), int(target_sr))
+    return resample_poly(wav, int(target_sr) // g, int(orig_sr) // g, axis=-1).astype(np.float32)
