@@ -1,0 +1,127 @@
+/* magicodec_b200.h — C ABI of the B200-native MagiCodec tokenization engine.
+ *
+ * This is the drop-in boundary of SURVEY.md §8(b).  The reference has no FFI of its own (it is
+ * pure Python over third-party PyTorch modules); each entry point below names the reference
+ * call it stands in for, file:line relative to /root/reference:
+ *
+ *   mc_create / mc_set_tensor / mc_finalize   load_magicodec_model(name, device)
+ *                                             realtime_codec_agent/audio_tokenizer.py:27-28
+ *   mc_encode                                 _magicodec_encode: pad_audio -> encoder ->
+ *                                             quantizer.inference          audio_tokenizer.py:189-194
+ *   mc_decode                                 _magicodec_decode: codebook_proj(codebook.weight) ->
+ *                                             F.embedding -> decoder       audio_tokenizer.py:196-201
+ *   mc_decode_latents                         model.decoder(z_q)           audio_tokenizer.py:200
+ *   mc_vq_search                              model.quantizer.inference    audio_tokenizer.py:192
+ *   mc_codebook                               quantizer.codebook_proj(quantizer.codebook.weight)
+ *                                                                          audio_tokenizer.py:158,198
+ *   mc_op_*                                   the library kernels underneath (cuDNN conv1d, cuBLAS /
+ *                                             fused_dense_lib linears, flash-attn local attention,
+ *                                             csrc/layer_norm, csrc/rotary; magicodec_build.sh:4-16)
+ *
+ * Conventions: every function returns 0 on success or a negative MC_ERR_* code and never throws
+ * or aborts; mc_last_error() gives the message.  All tensor arguments are DEVICE pointers owned by
+ * the caller (torch allocations on the host side); the library owns its handle, workspaces and
+ * cached TMA descriptors only.  Calls are asynchronous with respect to `stream` and do not
+ * synchronise (exception: a workspace that must grow synchronises the stream once).  A handle is
+ * not thread-safe: one handle per thread/stream.  sm_100 only — mc_create fails with MC_ERR_ARCH
+ * elsewhere; there is no CPU fallback.
+ */
+#ifndef MAGICODEC_B200_H_
+#define MAGICODEC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC_VERSION 100
+
+enum {
+  MC_OK = 0,
+  MC_ERR_ARG = -1,      /* bad argument / shape / missing tensor */
+  MC_ERR_ARCH = -2,     /* device is not sm_100 */
+  MC_ERR_CUDA = -3,     /* CUDA runtime / driver error (message has the detail) */
+  MC_ERR_STATE = -4,    /* call order (e.g. encode before finalize) */
+  MC_ERR_NOMEM = -5
+};
+
+typedef struct mc_handle mc_handle;
+typedef void* mc_stream_t; /* cudaStream_t */
+
+#define MC_MAX_CONVS 8
+
+typedef struct mc_spec {
+  int32_t sample_rate;
+  int32_t n_convs;                       /* encoder conv layers (decoder mirrors them)          */
+  int32_t conv_channels[MC_MAX_CONVS];   /* output channels of each encoder conv; last = d_model */
+  int32_t conv_strides[MC_MAX_CONVS];    /* kernel = 2*stride, causal                            */
+  int32_t d_model, n_heads, ffn_dim;
+  int32_t enc_layers, dec_layers;
+  int32_t window_left, window_right;     /* attention keys j in [i-wl, i+wr]                     */
+  float norm_eps;
+  int32_t codebook_size, codebook_dim;
+  int32_t max_positions;                 /* rows of the RoPE cos/sin tables                      */
+} mc_spec;
+
+int mc_version(void);
+const char* mc_last_error(const mc_handle* h); /* h may be NULL: error of the last failed mc_create */
+
+int mc_create(const mc_spec* spec, int device, mc_handle** out);
+int mc_destroy(mc_handle* h);
+
+/* Register one packed parameter (device pointer, kept by reference).  Names and layouts are listed
+ * in DESIGN.md §"Packed weights"; mc_finalize checks that all of them are present. */
+int mc_set_tensor(mc_handle* h, const char* name, const void* dev_ptr, int64_t numel);
+int mc_finalize(mc_handle* h);
+
+/* wav: fp32, B windows of T samples, window b starts at wav + b*ld (ld < T gives overlapping
+ * windows: the chunked encode of audio_tokenizer.py:52-65 is ld = chunk samples, T = context).
+ * T need not be a hop multiple (right zero padding = pad_audio).  F = ceil(T/hop).
+ * keep_last_frames: 0 = all F frames, else only the last k frames of each window are quantised.
+ * codes: int64 [B, Fk]; margin (optional): fp32 [B, Fk] = second-best minus best squared distance;
+ * z_e (optional): fp32 [B, F, dq] encoder output before quantisation. */
+int mc_encode(mc_handle* h, const float* wav, int64_t ld, int32_t B, int32_t T, int32_t keep_last_frames,
+              int64_t* codes, float* margin, float* z_e, mc_stream_t stream);
+
+/* codes: int64 [B, F].  keep_last_samples: 0 = all F*hop samples, else the last k (clamped).
+ * wav: fp32 [B, Tk]. */
+int mc_decode(mc_handle* h, const int64_t* codes, int32_t B, int32_t F, int32_t keep_last_samples, float* wav,
+              mc_stream_t stream);
+/* Same, entered with latents z_q fp32 [B, F, dq] (what F.embedding returns in the reference). */
+int mc_decode_latents(mc_handle* h, const float* z_q, int32_t B, int32_t F, int32_t keep_last_samples,
+                      float* wav, mc_stream_t stream);
+
+/* Nearest neighbour of each z row (fp32 [M, dq]) in the projected codebook. */
+int mc_vq_search(mc_handle* h, const float* z, int32_t M, int64_t* codes, float* margin, mc_stream_t stream);
+
+/* Copies the cached projected codebook, fp32 [K, dq]. */
+int mc_codebook(mc_handle* h, float* out, mc_stream_t stream);
+
+/* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
+int64_t mc_launch_count(const mc_handle* h);
+/* impl: 0 = tensor-core kernels (default), 1 = SIMT cross-check kernels for attention / VQ. */
+int mc_set_debug_impl(mc_handle* h, int32_t attention_impl, int32_t vq_impl);
+
+/* ---- operator level (each is one kernel launch; used by the parity tests and profiling) ---- */
+
+/* out[M,N] = epilogue(A * W^T).  A bf16 viewed as [a_rows, a_k_wrap] row blocks, K = multiple of
+ * a_k_wrap (see gemm_sm100.cuh); W bf16 [N,K]; bias fp32 [N] or NULL; act 0/1 (tanh-GELU);
+ * out_mode 0 bf16 / 1 fp32 / 2 fp32 residual (out += result); rope_period > 0 applies RoPE from the
+ * handle's tables to columns [0, rope_cols).  grp_in > 0 groups the M rows (grp_in per batch item, the
+ * first grp_valid of them stored) and writes row r of group g at out + g*grp_stride + grp_off + r*ldo
+ * (elements) — the implicit-GEMM convolutions; grp_in = 0 is a plain GEMM. */
+int mc_op_gemm(mc_handle* h, const void* A, int64_t a_rows, int32_t a_k_wrap, const void* W, const float* bias,
+               int32_t M, int32_t N, int32_t K, int32_t act, int32_t out_mode, void* out, int64_t ldo,
+               int32_t grp_in, int32_t grp_valid, int64_t grp_stride, int64_t grp_off, int32_t rope_cols,
+               int32_t rope_period, int32_t block_n, mc_stream_t stream);
+int mc_op_rmsnorm(mc_handle* h, const float* x, const float* gamma, void* out_bf16, int32_t M, int32_t d,
+                  mc_stream_t stream);
+/* qkv bf16 [B*F, 3*d] (RoPE applied) -> out bf16 [B*F, d]. */
+int mc_op_attention(mc_handle* h, const void* qkv, void* out, int32_t B, int32_t F, int32_t impl,
+                    mc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGICODEC_B200_H_ */

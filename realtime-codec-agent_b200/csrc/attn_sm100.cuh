@@ -1,0 +1,212 @@
+// Fused sliding-window attention on tcgen05, head_dim 64, causal window (keys j in [i-wl, i],
+// wl <= 32).  One CTA = 128 queries of one (window, head):
+//
+//   TMA   Q[128x64], K[160x64], V[160x64]  (keys q0-32 .. q0+127; out-of-tensor rows zero-filled)
+//   UMMA  S = Q K^T            128 x 160 x 64  -> TMEM cols [0,160)      (K-major A and B)
+//   SIMT  mask + softmax, one thread per query row, two passes over TMEM (max, then exp/sum);
+//         P (bf16) is written straight into the 128B-swizzled K-major layout UMMA reads
+//   UMMA  O = P V              128 x 64 x 160  -> TMEM cols [160,224)    (B = V, MN-major)
+//   SIMT  O / rowsum -> bf16 -> global
+//
+// S and P never touch HBM.  A window of <= 128 frames (every streaming / offline window: 100) is a
+// single tile; longer one-shot inputs tile along F with the 32-key halo.  ~105 KB smem and 256 TMEM
+// columns per CTA -> two CTAs per SM overlap each other's serial phases.
+#pragma once
+#include "engine_common.cuh"
+#include "gemm_sm100.cuh"
+
+namespace mc {
+
+constexpr int ATT_BQ = 128;    // queries per CTA
+constexpr int ATT_HALO = 32;   // keys before the first query
+constexpr int ATT_NKV = ATT_BQ + ATT_HALO;  // 160
+constexpr int ATT_THREADS = 128;
+constexpr int ATT_SMEM_Q = ATT_BQ * 128;        // 16384
+constexpr int ATT_SMEM_KV = ATT_NKV * 128;      // 20480
+constexpr int ATT_SMEM_P = 3 * ATT_BQ * 128;    // three 64-key atoms (the third half used)
+constexpr int ATT_SMEM_BYTES = ATT_SMEM_Q + 2 * ATT_SMEM_KV + ATT_SMEM_P + 64 + 1024;
+constexpr int ATT_TMEM_COLS = 256;
+
+inline bool attn_sm100_supported(int wl, int wr) { return wr == 0 && wl <= ATT_HALO; }
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_window_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                              __nv_bfloat16* __restrict__ out, int F, int H, int wl, float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATT_SMEM_Q;
+  uint8_t* sV = sK + ATT_SMEM_KV;
+  uint8_t* sP = sV + ATT_SMEM_KV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + ATT_SMEM_P);  // [0] tma, [1] S ready, [2] O ready
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tiles = (F + ATT_BQ - 1) / ATT_BQ;
+  const int q0 = (blockIdx.x % q_tiles) * ATT_BQ;
+  const int h = (blockIdx.x / q_tiles) % H;
+  const int b = blockIdx.x / (q_tiles * H);
+  const int d = H * 64;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_kv);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, ATT_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_s = tmem_base;
+  const uint32_t tmem_o = tmem_base + ATT_NKV;
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bars[0], ATT_SMEM_Q + 2 * ATT_SMEM_KV);
+    const int row_q = b * F + q0;
+    tma_load_2d(sQ, &map_q, &bars[0], h * 64, row_q);
+    tma_load_2d(sK, &map_kv, &bars[0], d + h * 64, row_q - ATT_HALO);
+    tma_load_2d(sV, &map_kv, &bars[0], 2 * d + h * 64, row_q - ATT_HALO);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, ATT_NKV, 0, 0);
+    const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ), 1024, 16);
+    const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sK), 1024, 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_s, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+    umma_commit(&bars[1]);
+  }
+  __syncwarp();
+
+  // ---- softmax: thread r owns query row q0 + r
+  const int r = threadIdx.x;
+  const int qi = q0 + r;
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+  // key column c <-> key index kj = q0 - HALO + c; valid iff 0 <= kj < F and qi - wl <= kj <= qi
+  const int c_lo = max(r + ATT_HALO - wl, ATT_HALO - q0);  // first valid column
+  const int c_hi = (qi < F) ? (r + ATT_HALO) : -1;         // last valid column (causal); none for padded rows
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c0 = 0; c0 < ATT_NKV; c0 += 32) {
+    uint32_t raw[32];
+    tmem_ld_32x32b_x32(tmem_s + lane_addr + c0, raw);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int c = c0 + j;
+      if (c >= c_lo && c <= c_hi) mx = fmaxf(mx, __uint_as_float(raw[j]));
+    }
+  }
+  const float mscaled = (mx == -INFINITY) ? 0.0f : mx * scale_log2e;
+  float sum = 0.0f;
+#pragma unroll 1
+  for (int c0 = 0; c0 < ATT_NKV; c0 += 32) {
+    uint32_t raw[32];
+    tmem_ld_32x32b_x32(tmem_s + lane_addr + c0, raw);
+    tmem_ld_wait();
+    uint32_t packed[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const int c = c0 + j;
+      float p0 = 0.0f, p1 = 0.0f;
+      if (c >= c_lo && c <= c_hi) p0 = exp2f(__uint_as_float(raw[j]) * scale_log2e - mscaled);
+      if (c + 1 >= c_lo && c + 1 <= c_hi) p1 = exp2f(__uint_as_float(raw[j + 1]) * scale_log2e - mscaled);
+      sum += p0 + p1;
+      packed[j >> 1] = pack_bf16x2(p0, p1);
+    }
+    // 32 keys = 4 chunks of 16 bytes inside atom (c0 / 64), chunk index ((c0 % 64) / 8 + u) ^ (r & 7)
+    uint8_t* atom = sP + (c0 >> 6) * (ATT_BQ * 128) + r * 128;
+    const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int chunk = (chunk0 + u) ^ (r & 7);
+      *reinterpret_cast<uint4*>(atom + chunk * 16) =
+          make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
+    }
+  }
+  fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, 64, 0, 1);  // B = V is MN-major
+#pragma unroll
+    for (int k = 0; k < ATT_NKV / 16; ++k) {
+      // A: P atom (k / 4), 32 bytes per 16-key step inside the atom
+      const uint64_t pdesc = umma_smem_desc_sw128(smem_u32(sP + (k >> 2) * (ATT_BQ * 128)) + (k & 3) * 32, 1024, 16);
+      // B: V rows are keys; 16 keys = 2048 bytes per step
+      const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sV) + k * 2048, 1024, 1024);
+      umma_bf16_ss(tmem_o, pdesc, vdesc, idesc_o, k != 0);
+    }
+    umma_commit(&bars[2]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[2], 0);
+  tc_fence_after();
+  {
+    uint32_t raw0[32], raw1[32];
+    tmem_ld_32x32b_x32(tmem_o + lane_addr, raw0);
+    tmem_ld_32x32b_x32(tmem_o + lane_addr + 32, raw1);
+    tmem_ld_wait();
+    if (qi < F) {
+      const float inv = 1.0f / sum;
+      __nv_bfloat16* o = out + (static_cast<long long>(b) * F + qi) * d + h * 64;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(raw0[j]) * inv, __uint_as_float(raw0[j + 1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(raw0[j + 2]) * inv, __uint_as_float(raw0[j + 3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(raw0[j + 4]) * inv, __uint_as_float(raw0[j + 5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(raw0[j + 6]) * inv, __uint_as_float(raw0[j + 7]) * inv);
+        *reinterpret_cast<uint4*>(o + j) = w;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(raw1[j]) * inv, __uint_as_float(raw1[j + 1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(raw1[j + 2]) * inv, __uint_as_float(raw1[j + 3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(raw1[j + 4]) * inv, __uint_as_float(raw1[j + 5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(raw1[j + 6]) * inv, __uint_as_float(raw1[j + 7]) * inv);
+        *reinterpret_cast<uint4*>(o + 32 + j) = w;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+  }
+}
+
+inline int launch_attention_sm100(mc_handle* h, const bf16* qkv, bf16* out, int B, int F, cudaStream_t stream) {
+  const mc_spec& s = h->spec;
+  const int d = s.d_model;
+  const CUtensorMap *mq, *mkv;
+  MC_TRY(mc_internal::get_map_2d_bf16(h, qkv, (uint64_t)3 * d, (uint64_t)B * F, 64, ATT_BQ, &mq));
+  MC_TRY(mc_internal::get_map_2d_bf16(h, qkv, (uint64_t)3 * d, (uint64_t)B * F, 64, ATT_NKV, &mkv));
+  static bool attr_set = false;
+  if (!attr_set) {
+    MC_CUDA(h, cudaFuncSetAttribute(attention_window_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    ATT_SMEM_BYTES));
+    attr_set = true;
+  }
+  const long long blocks = (long long)((F + ATT_BQ - 1) / ATT_BQ) * s.n_heads * B;
+  if (blocks > INT_MAX) return h->fail(MC_ERR_ARG, "attention: too many tiles");
+  const dim3 grid((unsigned)blocks);
+  attention_window_sm100_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(*mq, *mkv, out, F, s.n_heads, s.window_left,
+                                                                            0.125f * 1.4426950408889634f);
+  MC_LAUNCH_CHECK(h, "attention_window_sm100_kernel");
+  return MC_OK;
+}
+
+}  // namespace mc

@@ -1,0 +1,520 @@
+// Engine: sequences the kernels of one encode / decode pass over workspaces it owns and exports
+// the C ABI of include/magicodec_b200.h.
+#include "engine_common.cuh"
+
+#include "attn_sm100.cuh"
+#include "attn_vq_simt.cuh"
+#include "elementwise.cuh"
+#include "gemm_sm100.cuh"
+#include "vq_sm100.cuh"
+
+using namespace mc;
+using namespace mc_internal;
+
+namespace {
+
+// ------------------------------------------------------------------- GEMM
+struct GemmCall {
+  const bf16* A; int64_t a_rows; int a_k_wrap;
+  const bf16* W; const float* bias;
+  int M, N, K, act, out_mode;
+  void* out; int64_t ldo;
+  int grp_in = INT_MAX, grp_valid = INT_MAX; int64_t grp_stride = 0, grp_off = 0;
+  int rope_cols = 0, rope_period = 0;
+  int block_n = 0;  // 0 = choose
+};
+
+template <int BN>
+int launch_gemm_bn(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
+  const CUtensorMap *ma, *mb;
+  MC_TRY(get_map_2d_bf16(h, c.A, (uint64_t)c.a_k_wrap, (uint64_t)c.a_rows, GEMM_BK, GEMM_BM, &ma));
+  MC_TRY(get_map_2d_bf16(h, c.W, (uint64_t)c.K, (uint64_t)c.N, GEMM_BK, BN, &mb));
+  GemmParams p;
+  p.M = c.M; p.N = c.N; p.K = c.K; p.a_k_wrap = c.a_k_wrap;
+  p.bias = c.bias; p.act = c.act; p.out_mode = c.out_mode; p.out = c.out; p.ldo = c.ldo;
+  p.grp_in = c.grp_in; p.grp_valid = c.grp_valid; p.grp_stride = c.grp_stride; p.grp_off = c.grp_off;
+  p.rope_cols = c.rope_cols; p.rope_period = c.rope_period;
+  p.rope_cos = c.rope_period > 0 ? h->ptr<float>("rope.cos") : nullptr;
+  p.rope_sin = c.rope_period > 0 ? h->ptr<float>("rope.sin") : nullptr;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MC_CUDA(h, cudaFuncSetAttribute(gemm_bf16_sm100_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    GemmCfg<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  const int m_tiles = (c.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (c.N + BN - 1) / BN;
+  const int grid = std::min(m_tiles * n_tiles, h->num_sms);
+  gemm_bf16_sm100_kernel<BN><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, stream>>>(*ma, *mb, p);
+  MC_LAUNCH_CHECK(h, "gemm_bf16_sm100_kernel");
+  return MC_OK;
+}
+
+int launch_gemm(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
+  if (c.K % GEMM_BK != 0 || c.K % c.a_k_wrap != 0 || c.a_k_wrap % GEMM_BK != 0)
+    return h->fail(MC_ERR_ARG, "gemm: K=%d a_k_wrap=%d must be multiples of %d", c.K, c.a_k_wrap, GEMM_BK);
+  if (c.N % 8 != 0) return h->fail(MC_ERR_ARG, "gemm: N=%d must be a multiple of 8", c.N);
+  if (c.rope_period > 0 && c.rope_period > h->spec.max_positions)
+    return h->fail(MC_ERR_ARG, "gemm: rope period %d exceeds table rows %d", c.rope_period, h->spec.max_positions);
+  int bn = c.block_n;
+  if (bn == 0) {
+    const int m_tiles = (c.M + GEMM_BM - 1) / GEMM_BM;
+    if (c.N >= 256 && m_tiles * ((c.N + 255) / 256) >= 2 * h->num_sms) bn = 256;
+    else if (c.N >= 128 && m_tiles * ((c.N + 127) / 128) >= h->num_sms) bn = 128;
+    else if (c.N >= 256 && m_tiles * ((c.N + 255) / 256) >= h->num_sms) bn = 256;
+    else bn = 64;
+  }
+  switch (bn) {
+    case 256: return launch_gemm_bn<256>(h, c, stream);
+    case 128: return launch_gemm_bn<128>(h, c, stream);
+    case 64: return launch_gemm_bn<64>(h, c, stream);
+    default: return h->fail(MC_ERR_ARG, "gemm: unsupported block_n %d", bn);
+  }
+}
+
+int ew_grid(mc_handle* h, long long work_items, int threads) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = (long long)h->num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+int launch_rmsnorm(mc_handle* h, const float* x, const float* gamma, bf16* out, int M, int d, int grp_in,
+                   int64_t grp_stride, int64_t grp_off, cudaStream_t stream) {
+  if (d % 4 != 0) return h->fail(MC_ERR_ARG, "rmsnorm: d=%d must be a multiple of 4", d);
+  const int warps = 8;
+  const int grid = ew_grid(h, M, warps);
+  rmsnorm_kernel<<<grid, warps * 32, 0, stream>>>(x, gamma, out, M, d, h->spec.norm_eps, grp_in, grp_stride, grp_off);
+  MC_LAUNCH_CHECK(h, "rmsnorm_kernel");
+  return MC_OK;
+}
+
+int launch_attention(mc_handle* h, const bf16* qkv, bf16* out, int B, int F, int impl, cudaStream_t stream) {
+  const mc_spec& s = h->spec;
+  if (impl == 0 && attn_sm100_supported(s.window_left, s.window_right)) {
+    MC_TRY(launch_attention_sm100(h, qkv, out, B, F, stream));
+    return MC_OK;
+  }
+  if (s.window_left + s.window_right + 1 > 160) return h->fail(MC_ERR_ARG, "attention window too wide");
+  const long long warps = (long long)B * F * s.n_heads;
+  const int threads = 256;
+  const long long blocks = (warps * 32 + threads - 1) / threads;
+  attention_window_simt_kernel<<<(unsigned)blocks, threads, 0, stream>>>(qkv, out, B, F, s.n_heads, s.window_left,
+                                                                         s.window_right, 0.125f);
+  MC_LAUNCH_CHECK(h, "attention_window_simt_kernel");
+  return MC_OK;
+}
+
+// ------------------------------------------------------- transformer stack
+struct StackBufs {
+  float* x;   // [M,d] fp32 residual stream
+  bf16* hbuf; // [M,d]
+  bf16* qkv;  // [M,3d]
+  bf16* att;  // [M,d]
+  bf16* ffn;  // [M,f]
+};
+
+int run_layers(mc_handle* h, const char* prefix, int n_layers, const StackBufs& b, int B, int F, cudaStream_t stream) {
+  const mc_spec& s = h->spec;
+  const int M = B * F, d = s.d_model, f = s.ffn_dim;
+  char name[128];
+  for (int l = 0; l < n_layers; ++l) {
+    auto T = [&](const char* leaf) {
+      snprintf(name, sizeof(name), "%s.layers.%d.%s", prefix, l, leaf);
+      return std::string(name);
+    };
+    MC_TRY(launch_rmsnorm(h, b.x, h->ptr<float>(T("norm1")), b.hbuf, M, d, INT_MAX, 0, 0, stream));
+    GemmCall g{};
+    g.A = b.hbuf; g.a_rows = M; g.a_k_wrap = d; g.W = h->ptr<bf16>(T("wqkv")); g.bias = h->ptr<float>(T("bqkv"));
+    g.M = M; g.N = 3 * d; g.K = d; g.act = ACT_NONE; g.out_mode = OUT_BF16; g.out = b.qkv; g.ldo = 3 * d;
+    g.rope_cols = 2 * d; g.rope_period = F;
+    MC_TRY(launch_gemm(h, g, stream));
+    MC_TRY(launch_attention(h, b.qkv, b.att, B, F, h->attn_impl, stream));
+    GemmCall o{};
+    o.A = b.att; o.a_rows = M; o.a_k_wrap = d; o.W = h->ptr<bf16>(T("wo")); o.bias = h->ptr<float>(T("bo"));
+    o.M = M; o.N = d; o.K = d; o.act = ACT_NONE; o.out_mode = OUT_F32_RESIDUAL; o.out = b.x; o.ldo = d;
+    MC_TRY(launch_gemm(h, o, stream));
+    MC_TRY(launch_rmsnorm(h, b.x, h->ptr<float>(T("norm2")), b.hbuf, M, d, INT_MAX, 0, 0, stream));
+    GemmCall u{};
+    u.A = b.hbuf; u.a_rows = M; u.a_k_wrap = d; u.W = h->ptr<bf16>(T("w1")); u.bias = h->ptr<float>(T("b1"));
+    u.M = M; u.N = f; u.K = d; u.act = ACT_GELU_TANH; u.out_mode = OUT_BF16; u.out = b.ffn; u.ldo = f;
+    MC_TRY(launch_gemm(h, u, stream));
+    GemmCall w{};
+    w.A = b.ffn; w.a_rows = M; w.a_k_wrap = f; w.W = h->ptr<bf16>(T("w2")); w.bias = h->ptr<float>(T("b2"));
+    w.M = M; w.N = d; w.K = f; w.act = ACT_NONE; w.out_mode = OUT_F32_RESIDUAL; w.out = b.x; w.ldo = d;
+    MC_TRY(launch_gemm(h, w, stream));
+  }
+  return MC_OK;
+}
+
+StackBufs carve_stack(Carver& cv, uint8_t* base, int M, int d, int f, bool dry) {
+  StackBufs b{};
+  size_t ox = cv.take((size_t)M * d * 4), oh = cv.take((size_t)M * d * 2), oq = cv.take((size_t)M * 3 * d * 2),
+         oa = cv.take((size_t)M * d * 2), of = cv.take((size_t)M * f * 2);
+  if (!dry) {
+    b.x = reinterpret_cast<float*>(base + ox);
+    b.hbuf = reinterpret_cast<bf16*>(base + oh);
+    b.qkv = reinterpret_cast<bf16*>(base + oq);
+    b.att = reinterpret_cast<bf16*>(base + oa);
+    b.ffn = reinterpret_cast<bf16*>(base + of);
+  }
+  return b;
+}
+
+int launch_vq(mc_handle* h, const float* z, int n_items, int F, int keep, int64_t* codes, float* margin,
+              void* scratch, cudaStream_t stream);
+size_t vq_scratch_bytes(mc_handle* h, int Mq);
+
+// ----------------------------------------------------------------- encode
+int encode_impl(mc_handle* h, const float* wav, int64_t ld, int B, int T, int keep, int64_t* codes, float* margin,
+                float* z_e_out, cudaStream_t stream) {
+  const mc_spec& s = h->spec;
+  const int n = s.n_convs;
+  int hop = 1;
+  for (int i = 0; i < n; ++i) hop *= s.conv_strides[i];
+  const int F = (T + hop - 1) / hop;
+  if (F < 1) return h->fail(MC_ERR_ARG, "encode: empty input");
+  if (F > s.max_positions) return h->fail(MC_ERR_ARG, "encode: %d frames exceed RoPE table (%d rows)", F, s.max_positions);
+  if (keep <= 0 || keep > F) keep = F;
+  const int Tp = F * hop;
+  const int d = s.d_model, dq = s.codebook_dim;
+  const long long Mll = (long long)B * F;
+  if (Mll * std::max(3 * d, s.ffn_dim) > (long long)INT_MAX) return h->fail(MC_ERR_ARG, "encode: batch too large");
+  const int M = (int)Mll;
+
+  // per-layer time lengths and channel counts
+  std::vector<int> Tl(n), Cl(n);
+  {
+    int t = Tp;
+    for (int i = 0; i < n; ++i) { t /= s.conv_strides[i]; Tl[i] = t; Cl[i] = s.conv_channels[i]; }
+  }
+  // ---- carve workspace (two passes: size, then pointers)
+  std::vector<size_t> conv_off(n);
+  Carver cv;
+  for (int i = 0; i + 1 < n; ++i)
+    conv_off[i] = cv.take((size_t)B * (s.conv_strides[i + 1] + Tl[i]) * Cl[i] * 2 + 65536);
+  Carver cv2 = cv;
+  carve_stack(cv2, nullptr, M, d, s.ffn_dim, true);
+  size_t oz = cv2.take((size_t)M * dq * 4);
+  size_t ovq = cv2.take(vq_scratch_bytes(h, B * keep));
+  MC_TRY(arena_reserve(h, cv2.off, stream));
+  uint8_t* base = h->arena;
+  StackBufs sb = carve_stack(cv, base, M, d, s.ffn_dim, false);
+  float* z_e = reinterpret_cast<float*>(base + oz);
+  void* vq_scratch = base + ovq;
+
+  // ---- conv stack
+  for (int i = 0; i + 1 < n; ++i) {  // zero the left padding of every conv input
+    const int pad = s.conv_strides[i + 1];
+    const size_t pitch = (size_t)(pad + Tl[i]) * Cl[i] * 2;
+    MC_CUDA(h, cudaMemset2DAsync(base + conv_off[i], pitch, 0, (size_t)pad * Cl[i] * 2, B, stream));
+  }
+  {
+    const int s0 = s.conv_strides[0], C0 = Cl[0];
+    if (2 * s0 > 16 || C0 % 8 != 0) return h->fail(MC_ERR_ARG, "conv0: stride %d / channels %d unsupported", s0, C0);
+    const long long items = (long long)B * Tl[0] * (C0 / 8);
+    const int threads = 256;
+    const size_t smem = (size_t)(2 * s0 * C0 + C0) * 4;
+    conv_first_kernel<16><<<ew_grid(h, items, threads), threads, smem, stream>>>(
+        wav, ld, T, B, Tl[0], s0, C0, h->ptr<float>("enc.conv0.w"), h->ptr<float>("enc.conv0.b"),
+        reinterpret_cast<bf16*>(base + conv_off[0]), s.conv_strides[1]);
+    MC_LAUNCH_CHECK(h, "conv_first_kernel");
+  }
+  for (int i = 1; i < n; ++i) {
+    const int si = s.conv_strides[i];
+    GemmCall g{};
+    g.A = reinterpret_cast<const bf16*>(base + conv_off[i - 1]);
+    g.a_k_wrap = si * Cl[i - 1];
+    g.a_rows = (int64_t)B * (1 + Tl[i]);
+    g.W = h->ptr<bf16>("enc.conv" + std::to_string(i) + ".w");
+    g.bias = h->ptr<float>("enc.conv" + std::to_string(i) + ".b");
+    g.M = B * (1 + Tl[i]); g.N = Cl[i]; g.K = 2 * g.a_k_wrap;
+    g.grp_in = 1 + Tl[i]; g.grp_valid = Tl[i];
+    if (i + 1 < n) {
+      const int pad = s.conv_strides[i + 1];
+      g.act = ACT_GELU_TANH; g.out_mode = OUT_BF16; g.out = base + conv_off[i]; g.ldo = Cl[i];
+      g.grp_stride = (int64_t)(pad + Tl[i]) * Cl[i]; g.grp_off = (int64_t)pad * Cl[i];
+    } else {
+      g.act = ACT_NONE; g.out_mode = OUT_F32; g.out = sb.x; g.ldo = d;
+      g.grp_stride = (int64_t)F * d; g.grp_off = 0;
+    }
+    MC_TRY(launch_gemm(h, g, stream));
+  }
+  // ---- transformer
+  MC_TRY(run_layers(h, "enc", s.enc_layers, sb, B, F, stream));
+  MC_TRY(launch_rmsnorm(h, sb.x, h->ptr<float>("enc.norm_f"), sb.hbuf, M, d, INT_MAX, 0, 0, stream));
+  GemmCall pj{};
+  pj.A = sb.hbuf; pj.a_rows = M; pj.a_k_wrap = d; pj.W = h->ptr<bf16>("enc.proj.w"); pj.bias = h->ptr<float>("enc.proj.b");
+  pj.M = M; pj.N = dq; pj.K = d; pj.act = ACT_NONE; pj.out_mode = OUT_F32; pj.out = z_e; pj.ldo = dq;
+  MC_TRY(launch_gemm(h, pj, stream));
+  if (z_e_out) MC_CUDA(h, cudaMemcpyAsync(z_e_out, z_e, (size_t)M * dq * 4, cudaMemcpyDeviceToDevice, stream));
+  // ---- quantise the kept frames
+  MC_TRY(launch_vq(h, z_e, B, F, keep, codes, margin, vq_scratch, stream));
+  return MC_OK;
+}
+
+// ----------------------------------------------------------------- decode
+int decode_impl(mc_handle* h, const int64_t* codes, const float* z_q, int B, int F, int keep, float* wav,
+                cudaStream_t stream) {
+  const mc_spec& s = h->spec;
+  const int n = s.n_convs;
+  if (F < 1 || B < 1) return h->fail(MC_ERR_ARG, "decode: empty input");
+  if (F > s.max_positions) return h->fail(MC_ERR_ARG, "decode: %d frames exceed RoPE table (%d rows)", F, s.max_positions);
+  int hop = 1;
+  for (int i = 0; i < n; ++i) hop *= s.conv_strides[i];
+  const int d = s.d_model;
+  const long long Mll = (long long)B * F;
+  if (Mll * std::max(3 * d, s.ffn_dim) > (long long)INT_MAX) return h->fail(MC_ERR_ARG, "decode: batch too large");
+  const int M = (int)Mll;
+  const int total = F * hop;
+  if (keep <= 0 || keep > total) keep = total;
+  // decoder conv i: channels dch[i] -> dch[i+1], stride ds[i]; input length Tin[i]
+  std::vector<int> dch(n + 1), ds(n), Tin(n);
+  dch[0] = d;
+  for (int i = 0; i < n; ++i) {
+    ds[i] = s.conv_strides[n - 1 - i];
+    dch[i + 1] = (n - 2 - i >= 0) ? s.conv_channels[n - 2 - i] : 1;
+  }
+  Tin[0] = F;
+  for (int i = 1; i < n; ++i) Tin[i] = Tin[i - 1] * ds[i - 1];
+
+  Carver cv;
+  size_t oa0 = cv.take((size_t)M * 64 * 2);
+  std::vector<size_t> tb_off(n);
+  for (int i = 0; i < n; ++i) tb_off[i] = cv.take((size_t)B * (1 + Tin[i]) * dch[i] * 2 + 65536);
+  Carver cv2 = cv;
+  carve_stack(cv2, nullptr, M, d, s.ffn_dim, true);
+  MC_TRY(arena_reserve(h, cv2.off, stream));
+  uint8_t* base = h->arena;
+  StackBufs sb = carve_stack(cv, base, M, d, s.ffn_dim, false);
+  bf16* a0 = reinterpret_cast<bf16*>(base + oa0);
+
+  const int threads = 256;
+  if (codes) {
+    embed_codes_kernel<<<ew_grid(h, (long long)M * 8, threads), threads, 0, stream>>>(
+        reinterpret_cast<const long long*>(codes), h->ptr<float>("vq.codebook"), s.codebook_size, a0, M);
+    MC_LAUNCH_CHECK(h, "embed_codes_kernel");
+  } else {
+    pack_latents_kernel<<<ew_grid(h, (long long)M * 8, threads), threads, 0, stream>>>(z_q, a0, M);
+    MC_LAUNCH_CHECK(h, "pack_latents_kernel");
+  }
+  GemmCall ip{};
+  ip.A = a0; ip.a_rows = M; ip.a_k_wrap = 64; ip.W = h->ptr<bf16>("dec.in_proj.w"); ip.bias = h->ptr<float>("dec.in_proj.b");
+  ip.M = M; ip.N = d; ip.K = 64; ip.act = ACT_NONE; ip.out_mode = OUT_F32; ip.out = sb.x; ip.ldo = d;
+  MC_TRY(launch_gemm(h, ip, stream));
+  MC_TRY(run_layers(h, "dec", s.dec_layers, sb, B, F, stream));
+
+  for (int i = 0; i < n; ++i) {  // zero row 0 (left pad) of every transposed-conv input
+    const size_t pitch = (size_t)(1 + Tin[i]) * dch[i] * 2;
+    MC_CUDA(h, cudaMemset2DAsync(base + tb_off[i], pitch, 0, (size_t)dch[i] * 2, B, stream));
+  }
+  MC_TRY(launch_rmsnorm(h, sb.x, h->ptr<float>("dec.norm_f"), reinterpret_cast<bf16*>(base + tb_off[0]), M, d, F,
+                        (int64_t)(1 + F) * d, d, stream));
+  for (int i = 0; i + 1 < n; ++i) {
+    GemmCall g{};
+    g.A = reinterpret_cast<const bf16*>(base + tb_off[i]);
+    g.a_k_wrap = dch[i]; g.a_rows = (int64_t)B * (1 + Tin[i]);
+    g.W = h->ptr<bf16>("dec.up" + std::to_string(i) + ".w");
+    g.bias = h->ptr<float>("dec.up" + std::to_string(i) + ".b");
+    g.M = B * (1 + Tin[i]); g.N = ds[i] * dch[i + 1]; g.K = 2 * dch[i];
+    g.grp_in = 1 + Tin[i]; g.grp_valid = Tin[i];
+    g.act = ACT_GELU_TANH; g.out_mode = OUT_BF16; g.out = base + tb_off[i + 1]; g.ldo = g.N;
+    g.grp_stride = (int64_t)(1 + Tin[i + 1]) * dch[i + 1]; g.grp_off = dch[i + 1];
+    MC_TRY(launch_gemm(h, g, stream));
+  }
+  {
+    const int i = n - 1;
+    if (ds[i] > 8 || dch[i] % 8 != 0) return h->fail(MC_ERR_ARG, "last tconv: stride %d / channels %d unsupported", ds[i], dch[i]);
+    const long long items = (long long)B * Tin[i];
+    const size_t smem = (size_t)dch[i] * 2 * ds[i] * 4;
+    tconv_last_kernel<8><<<ew_grid(h, items, threads), threads, smem, stream>>>(
+        reinterpret_cast<const bf16*>(base + tb_off[i]), B, Tin[i], dch[i], ds[i],
+        h->ptr<float>("dec.up" + std::to_string(i) + ".w"), h->ptr<float>("dec.up" + std::to_string(i) + ".b"), wav, keep);
+    MC_LAUNCH_CHECK(h, "tconv_last_kernel");
+  }
+  return MC_OK;
+}
+
+// --------------------------------------------------------------------- VQ
+size_t vq_scratch_bytes(mc_handle* h, int Mq) {
+  return std::max(vq_sm100_scratch_bytes(h->num_sms, Mq), (size_t)64 * Mq * sizeof(VqPartial)) + 1024;
+}
+
+int launch_vq(mc_handle* h, const float* z, int n_items, int F, int keep, int64_t* codes, float* margin,
+              void* scratch, cudaStream_t stream) {
+  const mc_spec& s = h->spec;
+  const int Mq = n_items * keep;
+  if (h->vq_impl == 0) {
+    return launch_vq_sm100(h, z, n_items, F, keep, codes, margin, scratch, stream);
+  }
+  const int row_tiles = (Mq + 127) / 128;
+  int splits = (2 * h->num_sms + row_tiles - 1) / row_tiles;
+  splits = std::max(1, std::min(64, splits));
+  vq_simt_kernel<<<dim3(row_tiles, splits), 128, 0, stream>>>(z, Mq, F, keep, h->ptr<float>("vq.codebook"),
+                                                              h->ptr<float>("vq.c2"), s.codebook_size, splits,
+                                                              reinterpret_cast<VqPartial*>(scratch));
+  MC_LAUNCH_CHECK(h, "vq_simt_kernel");
+  vq_merge_kernel<<<(Mq + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const VqPartial*>(scratch), Mq, splits,
+                                                        reinterpret_cast<long long*>(codes), margin);
+  MC_LAUNCH_CHECK(h, "vq_merge_kernel");
+  return MC_OK;
+}
+
+std::vector<std::string> required_tensors(const mc_spec& s) {
+  std::vector<std::string> v;
+  const int n = s.n_convs;
+  for (int i = 0; i < n; ++i) {
+    v.push_back("enc.conv" + std::to_string(i) + ".w");
+    v.push_back("enc.conv" + std::to_string(i) + ".b");
+    v.push_back("dec.up" + std::to_string(i) + ".w");
+    v.push_back("dec.up" + std::to_string(i) + ".b");
+  }
+  const char* leaves[] = {"norm1", "wqkv", "bqkv", "wo", "bo", "norm2", "w1", "b1", "w2", "b2"};
+  for (int st = 0; st < 2; ++st)
+    for (int l = 0; l < (st == 0 ? s.enc_layers : s.dec_layers); ++l)
+      for (const char* leaf : leaves)
+        v.push_back(std::string(st == 0 ? "enc" : "dec") + ".layers." + std::to_string(l) + "." + leaf);
+  for (const char* nm : {"enc.norm_f", "enc.proj.w", "enc.proj.b", "vq.codebook", "vq.c2", "vq.packed", "dec.in_proj.w",
+                         "dec.in_proj.b", "dec.norm_f", "rope.cos", "rope.sin"})
+    v.push_back(nm);
+  return v;
+}
+
+}  // namespace
+
+// =============================================================== C ABI
+extern "C" {
+
+int mc_version(void) { return MC_VERSION; }
+
+const char* mc_last_error(const mc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int mc_create(const mc_spec* spec, int device, mc_handle** out) {
+  if (!spec || !out) { g_create_error = "mc_create: null argument"; return MC_ERR_ARG; }
+  *out = nullptr;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { g_create_error = std::string("mc_create: ") + cudaGetErrorString(e); return MC_ERR_CUDA; }
+  if (prop.major != 10) {
+    g_create_error = "mc_create: device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                     "; this library contains sm_100a code only (no fallback)";
+    return MC_ERR_ARCH;
+  }
+  if (spec->n_convs < 2 || spec->n_convs > MC_MAX_CONVS || spec->d_model % 64 != 0 || spec->d_model / spec->n_heads != 64 ||
+      spec->ffn_dim % 64 != 0 || spec->codebook_dim != 16 || spec->codebook_size % 256 != 0 ||
+      spec->conv_channels[spec->n_convs - 1] != spec->d_model) {
+    g_create_error = "mc_create: unsupported spec (need head_dim 64, d/ffn multiples of 64, codebook_dim 16)";
+    return MC_ERR_ARG;
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) { g_create_error = std::string("mc_create: ") + cudaGetErrorString(e); return MC_ERR_CUDA; }
+  mc_handle* h = new mc_handle();
+  h->spec = *spec;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  *out = h;
+  return MC_OK;
+}
+
+int mc_destroy(mc_handle* h) {
+  if (!h) return MC_OK;
+  if (h->arena) cudaFree(h->arena);
+  delete h;
+  return MC_OK;
+}
+
+int mc_set_tensor(mc_handle* h, const char* name, const void* dev_ptr, int64_t numel) {
+  if (!h || !name || !dev_ptr) return MC_ERR_ARG;
+  Tensor t; t.p = dev_ptr; t.numel = numel;
+  h->tensors[name] = t;
+  h->finalized = false;
+  return MC_OK;
+}
+
+int mc_finalize(mc_handle* h) {
+  if (!h) return MC_ERR_ARG;
+  for (const std::string& nm : required_tensors(h->spec))
+    if (!h->find(nm)) return h->fail(MC_ERR_ARG, "mc_finalize: tensor '%s' was not registered", nm.c_str());
+  h->finalized = true;
+  return MC_OK;
+}
+
+#define MC_ENTER(h)                                                        \
+  if (!(h)) return MC_ERR_ARG;                                             \
+  if (!(h)->finalized) return (h)->fail(MC_ERR_STATE, "handle not finalized"); \
+  { cudaError_t e__ = cudaSetDevice((h)->device); if (e__ != cudaSuccess) return (h)->fail(MC_ERR_CUDA, "cudaSetDevice failed"); }
+
+int mc_encode(mc_handle* h, const float* wav, int64_t ld, int32_t B, int32_t T, int32_t keep_last_frames,
+              int64_t* codes, float* margin, float* z_e, mc_stream_t stream) {
+  MC_ENTER(h);
+  if (!wav || !codes || B < 1 || T < 1) return h->fail(MC_ERR_ARG, "mc_encode: bad arguments (B=%d T=%d)", B, T);
+  return encode_impl(h, wav, ld, B, T, keep_last_frames, codes, margin, z_e, (cudaStream_t)stream);
+}
+
+int mc_decode(mc_handle* h, const int64_t* codes, int32_t B, int32_t F, int32_t keep_last_samples, float* wav,
+              mc_stream_t stream) {
+  MC_ENTER(h);
+  if (!codes || !wav) return h->fail(MC_ERR_ARG, "mc_decode: null pointer");
+  return decode_impl(h, codes, nullptr, B, F, keep_last_samples, wav, (cudaStream_t)stream);
+}
+
+int mc_decode_latents(mc_handle* h, const float* z_q, int32_t B, int32_t F, int32_t keep_last_samples, float* wav,
+                      mc_stream_t stream) {
+  MC_ENTER(h);
+  if (!z_q || !wav) return h->fail(MC_ERR_ARG, "mc_decode_latents: null pointer");
+  return decode_impl(h, nullptr, z_q, B, F, keep_last_samples, wav, (cudaStream_t)stream);
+}
+
+int mc_vq_search(mc_handle* h, const float* z, int32_t M, int64_t* codes, float* margin, mc_stream_t stream) {
+  MC_ENTER(h);
+  if (!z || !codes || M < 1) return h->fail(MC_ERR_ARG, "mc_vq_search: bad arguments");
+  Carver cv;
+  cv.take(vq_scratch_bytes(h, M));
+  MC_TRY(arena_reserve(h, cv.off, (cudaStream_t)stream));
+  return launch_vq(h, z, M, 1, 1, codes, margin, h->arena, (cudaStream_t)stream);
+}
+
+int mc_codebook(mc_handle* h, float* out, mc_stream_t stream) {
+  MC_ENTER(h);
+  const Tensor* t = h->find("vq.codebook");
+  MC_CUDA(h, cudaMemcpyAsync(out, t->p, (size_t)t->numel * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return MC_OK;
+}
+
+int64_t mc_launch_count(const mc_handle* h) { return h ? h->launches : 0; }
+
+int mc_set_debug_impl(mc_handle* h, int32_t attention_impl, int32_t vq_impl) {
+  if (!h) return MC_ERR_ARG;
+  h->attn_impl = attention_impl;
+  h->vq_impl = vq_impl;
+  return MC_OK;
+}
+
+int mc_op_gemm(mc_handle* h, const void* A, int64_t a_rows, int32_t a_k_wrap, const void* W, const float* bias,
+               int32_t M, int32_t N, int32_t K, int32_t act, int32_t out_mode, void* out, int64_t ldo,
+               int32_t grp_in, int32_t grp_valid, int64_t grp_stride, int64_t grp_off, int32_t rope_cols,
+               int32_t rope_period, int32_t block_n, mc_stream_t stream) {
+  MC_ENTER(h);
+  GemmCall g{};
+  g.A = reinterpret_cast<const bf16*>(A); g.a_rows = a_rows; g.a_k_wrap = a_k_wrap;
+  g.W = reinterpret_cast<const bf16*>(W); g.bias = bias; g.M = M; g.N = N; g.K = K; g.act = act; g.out_mode = out_mode;
+  g.out = out; g.ldo = ldo;
+  g.grp_in = grp_in > 0 ? grp_in : INT_MAX; g.grp_valid = grp_in > 0 ? grp_valid : INT_MAX;
+  g.grp_stride = grp_stride; g.grp_off = grp_off;
+  g.rope_cols = rope_cols; g.rope_period = rope_period; g.block_n = block_n;
+  return launch_gemm(h, g, (cudaStream_t)stream);
+}
+
+int mc_op_rmsnorm(mc_handle* h, const float* x, const float* gamma, void* out_bf16, int32_t M, int32_t d,
+                  mc_stream_t stream) {
+  MC_ENTER(h);
+  return launch_rmsnorm(h, x, gamma, reinterpret_cast<bf16*>(out_bf16), M, d, INT_MAX, 0, 0, (cudaStream_t)stream);
+}
+
+int mc_op_attention(mc_handle* h, const void* qkv, void* out, int32_t B, int32_t F, int32_t impl, mc_stream_t stream) {
+  MC_ENTER(h);
+  return launch_attention(h, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, F, impl,
+                          (cudaStream_t)stream);
+}
+
+}  // extern "C"

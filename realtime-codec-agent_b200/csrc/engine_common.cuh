@@ -1,0 +1,159 @@
+// Shared internals of the engine: the handle, error macros, workspace arena and the TMA
+// descriptor cache.  Included by engine.cu and by the kernel launchers (attn_sm100.cuh, vq_sm100.cuh).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <climits>
+#include <map>
+#include <string>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/magicodec_b200.h"
+#include "ptx_sm100.cuh"
+
+typedef __nv_bfloat16 bf16;
+
+namespace mc_internal {
+
+inline thread_local std::string g_create_error;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  }
+  return fn;
+}
+
+struct Tensor {
+  const void* p = nullptr;
+  int64_t numel = 0;
+};
+
+}  // namespace mc_internal
+using mc_internal::Tensor;
+
+struct mc_handle {
+  mc_spec spec{};
+  int device = 0;
+  int num_sms = 148;
+  bool finalized = false;
+  std::unordered_map<std::string, Tensor> tensors;
+  std::string err;
+  int64_t launches = 0;
+  int attn_impl = 0, vq_impl = 0;
+  // workspace arena
+  uint8_t* arena = nullptr;
+  size_t arena_cap = 0;
+  size_t arena_off = 0;
+  // TMA descriptor cache
+  std::map<std::tuple<const void*, uint64_t, uint64_t, uint32_t, uint32_t>, CUtensorMap> maps;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+  const Tensor* find(const std::string& name) const {
+    auto it = tensors.find(name);
+    return it == tensors.end() ? nullptr : &it->second;
+  }
+  template <typename T>
+  const T* ptr(const std::string& name) const {
+    return reinterpret_cast<const T*>(tensors.at(name).p);
+  }
+};
+
+#define MC_CUDA(h, expr)                                                                         \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      return (h)->fail(MC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define MC_TRY(expr)          \
+  do {                        \
+    int rc__ = (expr);        \
+    if (rc__ != MC_OK) return rc__; \
+  } while (0)
+#define MC_LAUNCH_CHECK(h, what)                                                                  \
+  do {                                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                                         \
+    if (e__ != cudaSuccess) return (h)->fail(MC_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e__)); \
+    (h)->launches++;                                                                              \
+  } while (0)
+
+namespace mc_internal {
+
+// ------------------------------------------------------------------ arena
+inline int arena_reserve(mc_handle* h, size_t bytes, cudaStream_t stream) {
+  if (bytes <= h->arena_cap) return MC_OK;
+  MC_CUDA(h, cudaStreamSynchronize(stream));
+  if (h->arena) MC_CUDA(h, cudaFree(h->arena));
+  h->arena = nullptr;
+  h->arena_cap = 0;
+  h->maps.clear();
+  const size_t cap = bytes + bytes / 8 + (1u << 20);
+  cudaError_t e = cudaMalloc(&h->arena, cap);
+  if (e != cudaSuccess) return h->fail(MC_ERR_NOMEM, "workspace cudaMalloc(%zu) failed: %s", cap, cudaGetErrorString(e));
+  h->arena_cap = cap;
+  return MC_OK;
+}
+struct Carver {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    const size_t at = off;
+    off += (bytes + 1023) & ~size_t(1023);
+    return at;
+  }
+};
+
+// ------------------------------------------------------------ TMA helpers
+inline int get_map_2d_bf16(mc_handle* h, const void* base, uint64_t dim0, uint64_t dim1, uint32_t box0, uint32_t box1,
+                    const CUtensorMap** out) {
+  auto key = std::make_tuple(base, dim0, dim1, box0, box1);
+  auto it = h->maps.find(key);
+  if (it != h->maps.end()) {
+    *out = &it->second;
+    return MC_OK;
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return h->fail(MC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (dim0 * 2) % 16 != 0)
+    return h->fail(MC_ERR_ARG, "TMA operand misaligned (base %p, row bytes %llu)", base, (unsigned long long)(dim0 * 2));
+  CUtensorMap m;
+  cuuint64_t gdim[2] = {dim0, dim1};
+  cuuint64_t gstride[1] = {dim0 * 2};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return h->fail(MC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) dims %llu x %llu box %u x %u", (int)r,
+                   (unsigned long long)dim0, (unsigned long long)dim1, box0, box1);
+  auto ins = h->maps.emplace(key, m);
+  *out = &ins.first->second;
+  return MC_OK;
+}
+
+}  // namespace mc_internal

@@ -1,0 +1,280 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  D[M,N] = epilogue(A[M,K] * W[N,K]^T)
+//
+//   warp 0      TMA producer     (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1      MMA issuer       (one thread: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16)
+//   warp 2      TMEM allocator   (2 x BN fp32 accumulator columns, double buffered)
+//   warps 4..7  epilogue         (tcgen05.ld -> bias / tanh-GELU / RoPE / residual -> global)
+//
+// The accumulator of tile i drains while the tensor pipe already works on tile i+1.
+//
+// Implicit-GEMM convolutions use the same kernel: A is addressed as a 2-D "row block" view
+// [rows, a_k_wrap]; K runs over `K / a_k_wrap` consecutive row blocks, i.e. k-block kb loads
+// box (k % a_k_wrap, row + k / a_k_wrap).  A causal conv with kernel 2*stride over a
+// channels-last buffer [.., stride*Cin] is then K = 2*stride*Cin with a_k_wrap = stride*Cin, and
+// a causal transposed conv is K = 2*Cin with a_k_wrap = Cin — no im2col buffer exists anywhere.
+// Rows are grouped (grp_in rows per batch item, of which grp_valid are real) so that the one
+// row per item that straddles the next item's left padding is computed but never stored.
+#pragma once
+#include "ptx_sm100.cuh"
+
+namespace mc {
+
+enum : int { ACT_NONE = 0, ACT_GELU_TANH = 1 };
+enum : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_RESIDUAL = 2 };
+
+struct GemmParams {
+  int M, N, K;
+  int a_k_wrap;
+  const float* bias;  // [N] or nullptr
+  int act;
+  int out_mode;
+  void* out;
+  long long ldo;  // elements between consecutive output rows
+  int grp_in, grp_valid;          // rows per batch item in A / how many of them are real
+  long long grp_stride, grp_off;  // output element offset = grp*grp_stride + grp_off + r*ldo
+  const float* rope_cos;  // [rope_period, 32] or nullptr
+  const float* rope_sin;
+  int rope_cols;    // RoPE applies to output columns [0, rope_cols), 64-wide heads
+  int rope_period;  // position = (row within group) % rope_period
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageBytesA = GEMM_BM * GEMM_BK * 2;
+  static constexpr int kStageBytesB = BN * GEMM_BK * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * (1.0f + t);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bar_base = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = p.K / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kStageBytesA;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          const int k_elem = kb * GEMM_BK;
+          const int row_off = k_elem / p.a_k_wrap;
+          const int a_k = k_elem - row_off * p.a_k_wrap;
+          tma_load_2d(sa, &map_a, &full_bar[stage], a_k, m_blk * GEMM_BM + row_off);
+          tma_load_2d(sb, &map_b, &full_bar[stage], k_elem, n_blk * BN);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kStageBytesA;
+          const uint64_t adesc = umma_smem_desc_sw128(sa, 1024, 16);
+          const uint64_t bdesc = umma_smem_desc_sw128(sb, 1024, 16);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // +32 bytes per K=16 step inside the 128-byte swizzled row (encoded >>4 -> +2)
+            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);      // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+
+      const int g = m_blk * GEMM_BM + q * 32 + lane;  // A row handled by this thread
+      const int grp = g / p.grp_in;
+      const int r = g - grp * p.grp_in;
+      const bool row_ok = (g < p.M) && (r < p.grp_valid);
+      const long long obase = static_cast<long long>(grp) * p.grp_stride + p.grp_off + static_cast<long long>(r) * p.ldo;
+      const int pos = (p.rope_period > 0) ? (r % p.rope_period) : 0;
+
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        const int n0 = n_blk * BN + c * 64;
+        if (n0 >= p.N) break;  // uniform across the warp
+        uint32_t raw0[32], raw1[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 64;
+        tmem_ld_32x32b_x32(taddr, raw0);
+        tmem_ld_32x32b_x32(taddr + 32, raw1);
+        tmem_ld_wait();
+        float v[64];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = __uint_as_float(raw0[j]);
+          v[32 + j] = __uint_as_float(raw1[j]);
+        }
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            if (n0 + j < p.N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+        }
+        if (p.act == ACT_GELU_TANH) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = gelu_tanh_f(v[j]);
+        }
+        if (p.rope_cos != nullptr && n0 < p.rope_cols) {
+          // one 64-wide head per chunk: rotate (j, j+32) by the angle of (pos, j)
+          const float4* c4 = reinterpret_cast<const float4*>(p.rope_cos + static_cast<long long>(pos) * 32);
+          const float4* s4 = reinterpret_cast<const float4*>(p.rope_sin + static_cast<long long>(pos) * 32);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 cc = __ldg(c4 + (j >> 2));
+            const float4 ss = __ldg(s4 + (j >> 2));
+            const float cs[4] = {cc.x, cc.y, cc.z, cc.w};
+            const float sn[4] = {ss.x, ss.y, ss.z, ss.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float x1 = v[j + u], x2 = v[32 + j + u];
+              v[j + u] = x1 * cs[u] - x2 * sn[u];
+              v[32 + j + u] = x1 * sn[u] + x2 * cs[u];
+            }
+          }
+        }
+        if (row_ok) {
+          if (p.out_mode == OUT_BF16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + n0;
+#pragma unroll
+            for (int j = 0; j < 64; j += 8) {
+              if (n0 + j < p.N) {
+                uint4 w;
+                w.x = pack_bf16x2(v[j], v[j + 1]);
+                w.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                w.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                w.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(o + j) = w;
+              }
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.out) + obase + n0;
+            if (p.out_mode == OUT_F32_RESIDUAL) {
+#pragma unroll
+              for (int j = 0; j < 64; j += 4) {
+                if (n0 + j < p.N) {
+                  float4 x = *reinterpret_cast<const float4*>(o + j);
+                  x.x += v[j]; x.y += v[j + 1]; x.z += v[j + 2]; x.w += v[j + 3];
+                  *reinterpret_cast<float4*>(o + j) = x;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 64; j += 4) {
+                if (n0 + j < p.N) {
+                  *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace mc

@@ -1,0 +1,144 @@
+"""GPU (B200): every kernel of the engine, one launch at a time through the C ABI, against plain
+PyTorch fp32 on the same device."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import realtime_codec_agent_b200 as pkg
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gen():
+    spec = pkg.MID_SPEC
+    return pkg.B200Generator(spec, pkg.init_random_weights(spec, seed=0), device="cuda", max_positions=1024)
+
+
+def _rand(shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(shape, generator=g, device="cuda") * scale
+
+
+def gelu_tanh(x):
+    return torch.nn.functional.gelu(x, approximate="tanh")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 256, 64), (100, 256, 128), (300, 1024, 256), (1000, 3072, 512),
+                                   (2560, 512, 2048), (77, 16, 512)])
+@pytest.mark.parametrize("block_n", [0, 64, 128, 256])
+def test_gemm_fp32_out(gen, M, N, K, block_n):
+    A = _rand((M, K), seed=1).to(torch.bfloat16)
+    W = (_rand((N, K), seed=2) / math.sqrt(K)).to(torch.bfloat16)
+    bias = _rand((N,), seed=3)
+    out = gen.op_gemm(A, W, bias=bias, out_mode=1, block_n=block_n)
+    ref = A.float() @ W.float().t() + bias
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("act", [0, 1])
+def test_gemm_bf16_out_bias_act(gen, act):
+    M, N, K = 515, 1024, 512
+    A = _rand((M, K), seed=4).to(torch.bfloat16)
+    W = (_rand((N, K), seed=5) / math.sqrt(K)).to(torch.bfloat16)
+    bias = _rand((N,), seed=6)
+    out = gen.op_gemm(A, W, bias=bias, act=act, out_mode=0)
+    ref = A.float() @ W.float().t() + bias
+    ref = gelu_tanh(ref) if act else ref
+    assert out.dtype == torch.bfloat16
+    assert (out.float() - ref).abs().max().item() < 0.03
+
+
+def test_gemm_residual_accumulates_in_place(gen):
+    M, N, K = 300, 512, 1024
+    A = _rand((M, K), seed=7).to(torch.bfloat16)
+    W = (_rand((N, K), seed=8) / math.sqrt(K)).to(torch.bfloat16)
+    bias = _rand((N,), seed=9)
+    x0 = _rand((M, N), seed=10)
+    x = x0.clone()
+    gen.op_gemm(A, W, bias=bias, out_mode=2, out=x)
+    ref = x0 + A.float() @ W.float().t() + bias
+    assert (x - ref).abs().max().item() < 2e-3
+
+
+def test_gemm_rope_epilogue(gen):
+    Fr, B, d = 100, 3, 512
+    M = B * Fr
+    A = _rand((M, 256), seed=11).to(torch.bfloat16)
+    W = (_rand((3 * d, 256), seed=12) / 16).to(torch.bfloat16)
+    out = gen.op_gemm(A, W, out_mode=1, rope_cols=2 * d, rope_period=Fr)
+    ref = (A.float() @ W.float().t()).view(B, Fr, 3, d // 64, 64)
+    cos, sin = gen._dev["rope.cos"][:Fr], gen._dev["rope.sin"][:Fr]
+
+    def rope(t):
+        x1, x2 = t[..., :32], t[..., 32:]
+        c, s = cos[None, :, None, :], sin[None, :, None, :]
+        return torch.cat((x1 * c - x2 * s, x1 * s + x2 * c), -1)
+
+    ref = torch.stack((rope(ref[:, :, 0]), rope(ref[:, :, 1]), ref[:, :, 2]), dim=2).reshape(M, 3 * d)
+    assert (out - ref).abs().max().item() < 2e-3
+
+
+def test_gemm_rowblock_conv_view_and_group_remap(gen):
+    """Implicit-GEMM conv: K spans two consecutive row blocks, one junk row per item is dropped and
+    the result lands behind the next layer's left padding."""
+    Bn, Tout, blk, N, pad_next = 3, 50, 128, 64, 4
+    rows = Bn * (1 + Tout)
+    buf = _rand((rows, blk), seed=13).to(torch.bfloat16)            # [B, 1+Tout, blk] row blocks
+    W = (_rand((N, 2 * blk), seed=14) / 16).to(torch.bfloat16)
+    bias = _rand((N,), seed=15)
+    out = torch.full((Bn, pad_next + Tout, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    gen.op_gemm(buf, W, bias=bias, act=1, out_mode=0, out=out, a_k_wrap=blk, M=rows, K=2 * blk, grp_in=1 + Tout,
+                grp_valid=Tout, grp_stride=(pad_next + Tout) * N, grp_off=pad_next * N, ldo=N)
+    flat = torch.cat([buf.reshape(-1), torch.zeros(blk, device="cuda", dtype=torch.bfloat16)])
+    idx = torch.arange(rows, device="cuda")[:, None] * blk + torch.arange(2 * blk, device="cuda")[None, :]
+    ref = gelu_tanh(flat[idx].float() @ W.float().t() + bias).view(Bn, 1 + Tout, N)[:, :Tout]
+    assert (out[:, pad_next:].float() - ref).abs().max().item() < 0.03
+    assert torch.all(out[:, :pad_next] == 7.0)                       # padding rows untouched
+
+
+def test_rmsnorm(gen):
+    x = _rand((333, 512), scale=3.0, seed=16)
+    g = 1.0 + 0.1 * _rand((512,), seed=17)
+    out = gen.op_rmsnorm(x, g)
+    ref = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + gen.spec.norm_eps) * g
+    assert (out.float() - ref).abs().max().item() < 0.03
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("B,Fr", [(1, 100), (3, 100), (2, 37), (1, 128), (2, 300)])
+def test_window_attention(gen, impl, B, Fr):
+    d, H = gen.spec.d_model, gen.spec.n_heads
+    qkv = _rand((B * Fr, 3 * d), seed=18).to(torch.bfloat16)
+    out = gen.op_attention(qkv, B, Fr, impl=impl)
+    t = qkv.float().view(B, Fr, 3, H, 64)
+    q, k, v = (t[:, :, i].transpose(1, 2) for i in range(3))
+    i = torch.arange(Fr, device="cuda")[:, None]
+    j = torch.arange(Fr, device="cuda")[None, :]
+    mask = (j >= i - gen.spec.window_left) & (j <= i + gen.spec.window_right)
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=mask, scale=0.125)
+    ref = ref.transpose(1, 2).reshape(B * Fr, d)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 0.03, f"impl {impl}: max abs err {err}"
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("M", [1, 5, 128, 1000])
+def test_vq_search(gen, impl, M):
+    gen.set_debug_impl(attention=0, vq=impl)
+    try:
+        z = _rand((M, 16), seed=19)
+        codes, margin = gen.vq_search(z, return_margin=True)
+    finally:
+        gen.set_debug_impl(0, 0)
+    cb = gen._dev["vq.codebook"].double()
+    dist = cb.pow(2).sum(-1)[None] - 2.0 * z.double() @ cb.t()
+    top2 = torch.topk(dist, 2, dim=-1, largest=False)
+    ref_margin = (top2.values[:, 1] - top2.values[:, 0]).float()
+    clear = ref_margin > 2e-3
+    assert torch.equal(codes[clear], top2.indices[:, 0][clear])
+    assert clear.float().mean().item() > 0.97
+    assert (margin - ref_margin).abs().max().item() < 2e-3

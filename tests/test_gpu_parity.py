@@ -1,0 +1,196 @@
+"""GPU (B200): whole-path parity of the CUDA engine against the fp32 oracle and the golden
+vectors made with the unmodified reference wrapper.
+
+Tolerances (BASELINE.json: "bit-exact wherever the reference fp32 distance margin exceeds a stated
+epsilon ... waveform within a stated max-abs and SNR"): the engine multiplies in bf16 with fp32
+accumulation (the reference's own GPU numerics: torch.autocast(bfloat16), audio_tokenizer.py:78-82),
+the oracle in fp32, so
+  * encoder latents:  max|z_e - z_e_oracle| <= Z_TOL
+  * codes: equal to the oracle's wherever the oracle's top-2 squared-distance margin > EPS_MARGIN;
+           frames under the margin are near-ties, counted and reported, at most NEAR_TIE_MAX of all
+  * decoded waveform (same codes in): SNR >= SNR_MIN_DB and max-abs error <= WAV_TOL x peak
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import realtime_codec_agent_b200 as pkg
+from oracle.magicodec_oracle import OracleGenerator
+
+pytestmark = pytest.mark.gpu
+
+Z_TOL = 0.08
+EPS_MARGIN = 0.35
+NEAR_TIE_MAX = 0.45
+SNR_MIN_DB = 30.0
+WAV_TOL = 0.05
+
+SPECS = {"tiny": pkg.TINY_SPEC, "mid": pkg.MID_SPEC}
+
+
+@pytest.fixture(scope="module", params=["tiny", "mid"])
+def bundle(request, golden_dir):
+    name = request.param
+    spec = SPECS[name]
+    w = pkg.init_random_weights(spec, seed=0)
+    g = np.load(os.path.join(golden_dir, f"golden_{name}.npz"))
+    gen = pkg.B200Generator(spec, w, device="cuda", max_positions=1024)
+    return name, spec, w, g, gen
+
+
+def _snr_db(ref, got):
+    noise = (ref - got).double().pow(2).sum().item()
+    sig = ref.double().pow(2).sum().item()
+    return 10.0 * np.log10(sig / max(noise, 1e-30))
+
+
+def _report(name, **kv):
+    print(f"[parity {name}] " + " ".join(f"{k}={v}" for k, v in kv.items()))
+
+
+def test_encode_taps_against_golden(bundle):
+    name, spec, w, g, gen = bundle
+    x = torch.from_numpy(np.stack([g["wav0"][-32000:], g["wav1"][-32000:]])).cuda()
+    codes, margin, z_e = gen.encode(x, return_margin=True, return_latents=True)
+    z_ref = torch.from_numpy(g["tap_z_e"]).cuda()
+    z_err = (z_e - z_ref).abs().max().item()
+    ref_idx = torch.from_numpy(g["tap_idx"]).long().cuda()
+    ref_margin = torch.from_numpy(g["tap_margin"]).cuda()
+    clear = ref_margin > EPS_MARGIN
+    agree_all = (codes == ref_idx).float().mean().item()
+    agree_clear = (codes[clear] == ref_idx[clear]).float().mean().item()
+    _report(name, z_err=round(z_err, 4), near_tie_frac=round(1 - clear.float().mean().item(), 3),
+            agree_all=round(agree_all, 3), agree_clear=round(agree_clear, 3))
+    assert z_err <= Z_TOL
+    assert torch.equal(codes[clear], ref_idx[clear])
+    assert 1 - clear.float().mean().item() <= NEAR_TIE_MAX
+    # the VQ stage by itself, fed the oracle's latents, is exact outside fp32-level ties
+    own = gen.vq_search(z_ref.reshape(-1, 16)).view(ref_idx.shape)
+    tight = ref_margin > 2e-3
+    assert torch.equal(own[tight], ref_idx[tight])
+
+
+def test_decode_against_golden(bundle):
+    name, spec, w, g, gen = bundle
+    ref_idx = torch.from_numpy(g["tap_idx"]).long().cuda()
+    rec = gen.decode(ref_idx)
+    ref = torch.from_numpy(g["tap_rec"]).cuda()
+    snr = _snr_db(ref, rec)
+    max_err = (rec - ref).abs().max().item() / ref.abs().max().item()
+    _report(name, decode_snr_db=round(snr, 1), decode_max_rel_err=round(max_err, 4))
+    assert snr >= SNR_MIN_DB and max_err <= WAV_TOL
+    # keep_last_samples == slicing the full output
+    tail = gen.decode(ref_idx, keep_last_samples=1920)
+    assert torch.equal(tail, rec[:, -1920:])
+
+
+def test_simt_and_tensor_core_paths_agree(bundle):
+    name, spec, w, g, gen = bundle
+    x = torch.from_numpy(np.stack([g["wav0"][-32000:], g["wav1"][-32000:]])).cuda()
+    c0, m0, z0 = gen.encode(x, return_margin=True, return_latents=True)
+    gen.set_debug_impl(attention=1, vq=1)
+    try:
+        c1, m1, z1 = gen.encode(x, return_margin=True, return_latents=True)
+    finally:
+        gen.set_debug_impl(0, 0)
+    assert (z0 - z1).abs().max().item() < 0.03
+    clear = torch.minimum(m0, m1) > 0.1
+    assert torch.equal(c0[clear], c1[clear])
+
+
+def test_batching_windows_and_keep_last_are_exact(bundle):
+    """Size-independent properties: per-window results do not depend on batch composition, on
+    reading windows through an overlapping strided view, or on asking only for the last frames."""
+    name, spec, w, g, gen = bundle
+    wav = torch.from_numpy(g["wav0"]).cuda()
+    n_win = 5
+    starts = [i * 1600 for i in range(n_win)]
+    windows = torch.stack([wav[s:s + 32000] for s in starts])
+    full = gen.encode(windows)                                             # [5,100]
+    single = torch.cat([gen.encode(windows[i:i + 1]) for i in range(n_win)])
+    assert torch.equal(full, single)
+    strided = gen.encode(wav, row_stride=1600, num_windows=n_win, window_samples=32000)
+    assert torch.equal(full, strided)
+    last5 = gen.encode(wav, row_stride=1600, num_windows=n_win, window_samples=32000, keep_last_frames=5)
+    assert torch.equal(full[:, -5:], last5)
+    again = gen.encode(windows)
+    assert torch.equal(full, again)                                        # deterministic run to run
+    # ragged length: 1 sample past a hop multiple -> one extra (zero padded) frame
+    assert gen.encode(wav[None, : 320 * 7 + 1]).shape == (1, 8)
+
+
+def test_reference_call_sequence_on_the_duck_type(bundle):
+    """The exact attribute/method sequence of audio_tokenizer.py:189-201 and :158 on B200Generator."""
+    name, spec, w, g, gen = bundle
+    x = torch.from_numpy(g["wav0"][-32000:][None]).cuda()
+    with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+        z_e = gen.encoder(gen.pad_audio(x))
+        _, idx = gen.quantizer.inference(z_e)
+        idx = idx.unsqueeze(1)
+        table = gen.quantizer.codebook_proj(gen.quantizer.codebook.weight)
+        z_q = torch.nn.functional.embedding(idx.squeeze(1), table)
+        rec = gen.decoder(z_q).float()
+    assert idx.shape == (1, 1, 100) and rec.shape == (1, 1, 32000)
+    assert table.dtype == torch.bfloat16 and table.shape == (spec.codebook_size, 16)
+    assert torch.equal(idx[0, 0], gen.encode(x)[0])
+    direct = gen.decode(idx[0])
+    assert _snr_db(direct, rec[0]) > 35.0          # bf16 vs fp32 latents entering the decoder
+
+
+def test_native_audio_tokenizer_streaming(bundle):
+    """Our AudioTokenizer on the native engine: chunked 0.1 s encode + streaming decode against the
+    golden run of the unmodified reference wrapper (margin-qualified)."""
+    name, spec, w, g, gen = bundle
+    oracle = OracleGenerator(spec, w)
+    tok = pkg.AudioTokenizer(codec_model=gen, device="cuda")
+    assert tok.framerate == 50.0 and tok.context_samples == 32000 and tok.context_frames == 100
+    wav0 = g["wav0"]
+    s = tok.chunked_tokenize_audio(wav0, 0.1)
+    got = np.array([ord(c) - tok.unicode_offset for c in s])
+    ref = g["mono_chunked_codes"]
+    assert got.shape == ref.shape
+    with torch.no_grad():                                   # oracle margins for the one-shot pass (same frames
+        z = oracle.encoder(oracle.pad_audio(torch.from_numpy(wav0[None])))   # wherever context is untruncated)
+        _, idx, margin = oracle.quantizer.inference(z, return_margin=True)
+    clear = (margin[0].numpy() > EPS_MARGIN) & (idx[0].numpy() == ref)
+    _report(name, stream_agree_all=round(float((got == ref).mean()), 3), stream_clear_frac=round(float(clear.mean()), 3))
+    assert np.array_equal(got[clear], ref[clear])
+    tok.reset_context()
+    ref_str = "".join(chr(int(c) + tok.unicode_offset) for c in ref)
+    pieces = []
+    for i in range(0, len(ref_str), 5):
+        (sr, rec), hang, pre = tok.detokenize_audio(ref_str[i:i + 5], preroll_samples=320)
+        assert sr == 16000 and hang == ""
+        assert rec.shape[-1] == min(1920, (i // 5 + 1) * 1600)
+        pieces.append(rec[-1600:])
+    rec = torch.from_numpy(np.concatenate(pieces))
+    assert _snr_db(torch.from_numpy(g["mono_stream_decode_wav"]), rec) >= SNR_MIN_DB
+    # stereo: both channels in one batched call, interleaved chars
+    tok2 = pkg.AudioTokenizer(codec_model=gen, num_channels=2, device="cuda")
+    st = np.stack([g["wav0"], g["wav1"]])
+    s2 = tok2.chunked_tokenize_audio(st, 0.1)
+    assert len(s2) == len(g["stereo_chunked_codes"])
+    assert s2[0::2] == s                                       # channel 0 of the stereo stream == the mono stream
+    (sr, rec2), hang, pre = tok2.detokenize_audio(s2[:201])
+    assert rec2.shape == g["stereo_decode_wav"].shape and len(hang) == 1
+
+
+def test_default_spec_shapes_and_determinism():
+    """BASELINE config shapes on the full-size default spec (no oracle at this size)."""
+    spec = pkg.DEFAULT_SPEC
+    gen = pkg.B200Generator(spec, pkg.init_random_weights(spec, seed=0), device="cuda")
+    wav = pkg.synth_audio(16000 * 12, device="cuda")
+    codes = gen.encode(wav, row_stride=1600, num_windows=64, window_samples=32000, keep_last_frames=5)
+    assert codes.shape == (64, 5) and codes.min() >= 0 and codes.max() < spec.codebook_size
+    assert torch.equal(codes, gen.encode(wav, row_stride=1600, num_windows=64, window_samples=32000, keep_last_frames=5))
+    one = gen.encode(wav[1600 * 7: 1600 * 7 + 32000][None], keep_last_frames=5)
+    assert torch.equal(one[0], codes[7])
+    rec = gen.decode(codes.reshape(2, 160))
+    assert rec.shape == (2, 160 * 320) and torch.isfinite(rec).all()
+    tok = pkg.AudioTokenizer(codec_model=gen, device="cuda")
+    assert tok.framerate == 50.0
+    assert len(tok.tokenize_audio(wav[:1600].cpu().numpy())) == 5
+    emb = tok.get_codec_embeddings()
+    assert emb.shape == (131072, 16) and torch.equal(emb, tok.get_codec_embeddings())
