@@ -100,6 +100,12 @@ int mc_codebook(mc_handle* h, float* out, mc_stream_t stream);
 
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t mc_launch_count(const mc_handle* h);
+/* Device timing by kernel class (0 GEMM, 1 attention, 2 VQ search, 3 HBM-bound elementwise): between
+ * begin and end every launch is bracketed by a CUDA event pair on its stream; end synchronises on
+ * those events and returns, per class, the summed milliseconds, algorithmic FLOPs and bytes, and
+ * the launch count.  Used by bench.py for the roofline object; off by default. */
+int mc_profile_begin(mc_handle* h);
+int mc_profile_end(mc_handle* h, double* ms, double* flops, double* bytes, int64_t* launches, int32_t n_classes);
 /* impl: 0 = tensor-core kernels (default), 1 = SIMT cross-check kernels for attention / VQ. */
 int mc_set_debug_impl(mc_handle* h, int32_t attention_impl, int32_t vq_impl);
 

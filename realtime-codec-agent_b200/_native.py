@@ -47,6 +47,8 @@ SYMBOLS = {
     "mc_codebook": (C.c_int, [_P, _P, _P]),
     "mc_launch_count": (_I64, [_P]),
     "mc_set_debug_impl": (C.c_int, [_P, _I32, _I32]),
+    "mc_profile_begin": (C.c_int, [_P]),
+    "mc_profile_end": (C.c_int, [_P, _P, _P, _P, _P, _I32]),
     "mc_op_gemm": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _I64,
                              _I32, _I32, _I64, _I64, _I32, _I32, _I32, _P]),
     "mc_op_rmsnorm": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P]),

@@ -44,6 +44,9 @@ int launch_gemm_bn(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   }
   const int m_tiles = (c.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (c.N + BN - 1) / BN;
   const int grid = std::min(m_tiles * n_tiles, h->num_sms);
+  const double valid_rows = c.grp_in == INT_MAX ? (double)c.M : (double)c.M / c.grp_in * c.grp_valid;
+  const double out_bytes = valid_rows * c.N * (c.out_mode == OUT_BF16 ? 2.0 : (c.out_mode == OUT_F32 ? 4.0 : 8.0));
+  McProfScope prof(h, 0, 2.0 * valid_rows * c.N * c.K, valid_rows * c.a_k_wrap * 2.0 + (double)c.N * c.K * 2.0 + out_bytes, stream);
   gemm_bf16_sm100_kernel<BN><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, stream>>>(*ma, *mb, p);
   MC_LAUNCH_CHECK(h, "gemm_bf16_sm100_kernel");
   return MC_OK;
@@ -84,6 +87,7 @@ int launch_rmsnorm(mc_handle* h, const float* x, const float* gamma, bf16* out, 
   if (d % 4 != 0) return h->fail(MC_ERR_ARG, "rmsnorm: d=%d must be a multiple of 4", d);
   const int warps = 8;
   const int grid = ew_grid(h, M, warps);
+  McProfScope prof(h, 3, 0.0, (double)M * d * 6.0, stream);
   rmsnorm_kernel<<<grid, warps * 32, 0, stream>>>(x, gamma, out, M, d, h->spec.norm_eps, grp_in, grp_stride, grp_off);
   MC_LAUNCH_CHECK(h, "rmsnorm_kernel");
   return MC_OK;
@@ -91,6 +95,8 @@ int launch_rmsnorm(mc_handle* h, const float* x, const float* gamma, bf16* out, 
 
 int launch_attention(mc_handle* h, const bf16* qkv, bf16* out, int B, int F, int impl, cudaStream_t stream) {
   const mc_spec& s = h->spec;
+  const double span = std::min(F, s.window_left + s.window_right + 1);
+  McProfScope prof(h, 1, 4.0 * B * F * span * s.d_model, (double)B * F * s.d_model * 8.0, stream);
   if (impl == 0 && attn_sm100_supported(s.window_left, s.window_right)) {
     MC_TRY(launch_attention_sm100(h, qkv, out, B, F, stream));
     return MC_OK;
@@ -215,6 +221,7 @@ int encode_impl(mc_handle* h, const float* wav, int64_t ld, int B, int T, int ke
     const long long items = (long long)B * Tl[0] * (C0 / 8);
     const int threads = 256;
     const size_t smem = (size_t)(2 * s0 * C0 + C0) * 4;
+    McProfScope prof(h, 3, 2.0 * B * Tl[0] * 2 * s0 * C0, (double)B * T * 4.0 + (double)B * Tl[0] * C0 * 2.0, stream);
     conv_first_kernel<16><<<ew_grid(h, items, threads), threads, smem, stream>>>(
         wav, ld, T, B, Tl[0], s0, C0, h->ptr<float>("enc.conv0.w"), h->ptr<float>("enc.conv0.b"),
         reinterpret_cast<bf16*>(base + conv_off[0]), s.conv_strides[1]);
@@ -327,6 +334,7 @@ int decode_impl(mc_handle* h, const int64_t* codes, const float* z_q, int B, int
     if (ds[i] > 8 || dch[i] % 8 != 0) return h->fail(MC_ERR_ARG, "last tconv: stride %d / channels %d unsupported", ds[i], dch[i]);
     const long long items = (long long)B * Tin[i];
     const size_t smem = (size_t)dch[i] * 2 * ds[i] * 4;
+    McProfScope prof(h, 3, 4.0 * B * Tin[i] * dch[i] * ds[i], (double)B * Tin[i] * dch[i] * 2.0 + (double)B * keep * 4.0, stream);
     tconv_last_kernel<8><<<ew_grid(h, items, threads), threads, smem, stream>>>(
         reinterpret_cast<const bf16*>(base + tb_off[i]), B, Tin[i], dch[i], ds[i],
         h->ptr<float>("dec.up" + std::to_string(i) + ".w"), h->ptr<float>("dec.up" + std::to_string(i) + ".b"), wav, keep);
@@ -344,6 +352,7 @@ int launch_vq(mc_handle* h, const float* z, int n_items, int F, int keep, int64_
               void* scratch, cudaStream_t stream) {
   const mc_spec& s = h->spec;
   const int Mq = n_items * keep;
+  McProfScope prof(h, 2, 2.0 * Mq * (double)s.codebook_size * s.codebook_dim, (double)s.codebook_size * 128.0, stream);
   if (h->vq_impl == 0) {
     return launch_vq_sm100(h, z, n_items, F, keep, codes, margin, scratch, stream);
   }
@@ -482,6 +491,30 @@ int mc_codebook(mc_handle* h, float* out, mc_stream_t stream) {
 }
 
 int64_t mc_launch_count(const mc_handle* h) { return h ? h->launches : 0; }
+
+int mc_profile_begin(mc_handle* h) {
+  if (!h) return MC_ERR_ARG;
+  for (auto& r : h->prof) { h->event_pool.push_back(r.a); h->event_pool.push_back(r.b); }
+  h->prof.clear();
+  h->profiling = true;
+  return MC_OK;
+}
+
+int mc_profile_end(mc_handle* h, double* ms, double* flops, double* bytes, int64_t* launches, int32_t n_classes) {
+  if (!h || !ms || !flops || !bytes || !launches) return MC_ERR_ARG;
+  h->profiling = false;
+  for (int c = 0; c < n_classes; ++c) { ms[c] = 0; flops[c] = 0; bytes[c] = 0; launches[c] = 0; }
+  for (auto& r : h->prof) {
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e != cudaSuccess) return h->fail(MC_ERR_CUDA, "mc_profile_end: %s", cudaGetErrorString(e));
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    if (r.cls < n_classes) { ms[r.cls] += t; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes; launches[r.cls]++; }
+    h->event_pool.push_back(r.a); h->event_pool.push_back(r.b);
+  }
+  h->prof.clear();
+  return MC_OK;
+}
 
 int mc_set_debug_impl(mc_handle* h, int32_t attention_impl, int32_t vq_impl) {
   if (!h) return MC_ERR_ARG;

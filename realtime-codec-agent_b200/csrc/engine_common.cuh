@@ -58,6 +58,11 @@ struct mc_handle {
   std::string err;
   int64_t launches = 0;
   int attn_impl = 0, vq_impl = 0;
+  // optional per-class device timing (bench.py's roofline): event pairs around each launch
+  struct ProfRec { cudaEvent_t a, b; int cls; double flops; double bytes; };
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> event_pool;
   // workspace arena
   uint8_t* arena = nullptr;
   size_t arena_cap = 0;
@@ -95,6 +100,26 @@ struct mc_handle {
     int rc__ = (expr);        \
     if (rc__ != MC_OK) return rc__; \
   } while (0)
+// Kernel classes for mc_profile_*: 0 GEMM (tcgen05), 1 attention, 2 VQ search, 3 HBM-bound elementwise
+struct McProfScope {
+  mc_handle* h; cudaStream_t st; bool on;
+  mc_handle::ProfRec rec;
+  static cudaEvent_t get_event(mc_handle* h) {
+    if (!h->event_pool.empty()) { cudaEvent_t e = h->event_pool.back(); h->event_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  McProfScope(mc_handle* h_, int cls, double flops, double bytes, cudaStream_t s) : h(h_), st(s), on(h_->profiling) {
+    if (!on) return;
+    rec.a = get_event(h); rec.b = get_event(h); rec.cls = cls; rec.flops = flops; rec.bytes = bytes;
+    cudaEventRecord(rec.a, st);
+  }
+  ~McProfScope() {
+    if (!on) return;
+    cudaEventRecord(rec.b, st);
+    h->prof.push_back(rec);
+  }
+};
+
 #define MC_LAUNCH_CHECK(h, what)                                                                  \
   do {                                                                                            \
     cudaError_t e__ = cudaGetLastError();                                                         \

@@ -224,6 +224,20 @@ class B200Generator:
     def set_debug_impl(self, attention: int = 0, vq: int = 0) -> None:
         nat.check(self._lib, self._handle, self._lib.mc_set_debug_impl(self._handle, attention, vq), "mc_set_debug_impl")
 
+    PROFILE_CLASSES = ("gemm", "attention", "vq", "elementwise")
+
+    def profile_begin(self) -> None:
+        nat.check(self._lib, self._handle, self._lib.mc_profile_begin(self._handle), "mc_profile_begin")
+
+    def profile_end(self) -> Dict[str, Dict[str, float]]:
+        n = len(self.PROFILE_CLASSES)
+        ms, fl, by = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        rc = self._lib.mc_profile_end(self._handle, ms, fl, by, cnt, n)
+        nat.check(self._lib, self._handle, rc, "mc_profile_end")
+        return {name: {"ms": ms[i], "flops": fl[i], "bytes": by[i], "launches": int(cnt[i])}
+                for i, name in enumerate(self.PROFILE_CLASSES)}
+
     # ---- fast batched entry points
     def encode(self, wav: torch.Tensor, keep_last_frames: int = 0, return_margin: bool = False,
                return_latents: bool = False, row_stride: Optional[int] = None, num_windows: Optional[int] = None,
