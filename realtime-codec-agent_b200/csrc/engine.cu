@@ -29,7 +29,15 @@ int launch_gemm_bn(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   const CUtensorMap *ma, *mb;
   MC_TRY(get_map_2d_bf16(h, c.A, (uint64_t)c.a_k_wrap, (uint64_t)c.a_rows, GEMM_BK, GEMM_BM, &ma));
   MC_TRY(get_map_2d_bf16(h, c.W, (uint64_t)c.K, (uint64_t)c.N, GEMM_BK, BN, &mb));
+  // plain (ungrouped) outputs leave through TMA: bf16 boxes of 64 columns, fp32 boxes of 32
+  const bool tma_out = (c.grp_in == INT_MAX);
+  const CUtensorMap* mo = ma;
+  if (tma_out) {
+    const int esize = c.out_mode == OUT_BF16 ? 2 : 4;
+    MC_TRY(get_map_2d(h, c.out, esize, (uint64_t)c.N, (uint64_t)c.M, (uint64_t)c.ldo * esize, esize == 2 ? 64 : 32, 32, &mo));
+  }
   GemmParams p;
+  p.tma_store = tma_out ? 1 : 0;
   p.M = c.M; p.N = c.N; p.K = c.K; p.a_k_wrap = c.a_k_wrap;
   p.bias = c.bias; p.act = c.act; p.out_mode = c.out_mode; p.out = c.out; p.ldo = c.ldo;
   p.grp_in = c.grp_in; p.grp_valid = c.grp_valid; p.grp_stride = c.grp_stride; p.grp_off = c.grp_off;
@@ -47,7 +55,7 @@ int launch_gemm_bn(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   const double valid_rows = c.grp_in == INT_MAX ? (double)c.M : (double)c.M / c.grp_in * c.grp_valid;
   const double out_bytes = valid_rows * c.N * (c.out_mode == OUT_BF16 ? 2.0 : (c.out_mode == OUT_F32 ? 4.0 : 8.0));
   McProfScope prof(h, 0, 2.0 * valid_rows * c.N * c.K, valid_rows * c.a_k_wrap * 2.0 + (double)c.N * c.K * 2.0 + out_bytes, stream);
-  gemm_bf16_sm100_kernel<BN><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, stream>>>(*ma, *mb, p);
+  gemm_bf16_sm100_kernel<BN><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, stream>>>(*ma, *mb, *mo, p);
   MC_LAUNCH_CHECK(h, "gemm_bf16_sm100_kernel");
   return MC_OK;
 }

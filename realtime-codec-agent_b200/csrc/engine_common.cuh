@@ -68,7 +68,7 @@ struct mc_handle {
   size_t arena_cap = 0;
   size_t arena_off = 0;
   // TMA descriptor cache
-  std::map<std::tuple<const void*, uint64_t, uint64_t, uint32_t, uint32_t>, CUtensorMap> maps;
+  std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t>, CUtensorMap> maps;
 
   int fail(int code, const char* fmt, ...) {
     char buf[1024];
@@ -153,9 +153,11 @@ struct Carver {
 };
 
 // ------------------------------------------------------------ TMA helpers
-inline int get_map_2d_bf16(mc_handle* h, const void* base, uint64_t dim0, uint64_t dim1, uint32_t box0, uint32_t box1,
-                    const CUtensorMap** out) {
-  auto key = std::make_tuple(base, dim0, dim1, box0, box1);
+// 2-D tiled, 128B-swizzled tensor map over a row-major [dim1, dim0] array of `esize`-byte elements
+// with `row_stride_bytes` between rows (esize 2 = bf16, 4 = fp32).
+inline int get_map_2d(mc_handle* h, const void* base, int esize, uint64_t dim0, uint64_t dim1, uint64_t row_stride_bytes,
+                      uint32_t box0, uint32_t box1, const CUtensorMap** out) {
+  auto key = std::make_tuple(base, dim0, dim1, row_stride_bytes, (uint32_t)(box0 | (esize << 16)), box1);
   auto it = h->maps.find(key);
   if (it != h->maps.end()) {
     *out = &it->second;
@@ -163,22 +165,26 @@ inline int get_map_2d_bf16(mc_handle* h, const void* base, uint64_t dim0, uint64
   }
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return h->fail(MC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (dim0 * 2) % 16 != 0)
-    return h->fail(MC_ERR_ARG, "TMA operand misaligned (base %p, row bytes %llu)", base, (unsigned long long)(dim0 * 2));
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || row_stride_bytes % 16 != 0 || box0 * esize > 128)
+    return h->fail(MC_ERR_ARG, "TMA operand misaligned (base %p, row stride %llu B, box %u x %d B)", base,
+                   (unsigned long long)row_stride_bytes, box0, esize);
   CUtensorMap m;
   cuuint64_t gdim[2] = {dim0, dim1};
-  cuuint64_t gstride[1] = {dim0 * 2};
+  cuuint64_t gstride[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box0, box1};
   cuuint32_t estride[2] = {1, 1};
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(&m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return h->fail(MC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) dims %llu x %llu box %u x %u", (int)r,
-                   (unsigned long long)dim0, (unsigned long long)dim1, box0, box1);
+    return h->fail(MC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) dims %llu x %llu box %u x %u esize %d", (int)r,
+                   (unsigned long long)dim0, (unsigned long long)dim1, box0, box1, esize);
   auto ins = h->maps.emplace(key, m);
   *out = &ins.first->second;
   return MC_OK;
 }
-
+inline int get_map_2d_bf16(mc_handle* h, const void* base, uint64_t dim0, uint64_t dim1, uint32_t box0, uint32_t box1,
+                           const CUtensorMap** out) {
+  return get_map_2d(h, base, 2, dim0, dim1, dim0 * 2, box0, box1, out);
+}
 }  // namespace mc_internal

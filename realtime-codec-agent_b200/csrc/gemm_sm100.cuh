@@ -32,6 +32,7 @@ struct GemmParams {
   long long ldo;  // elements between consecutive output rows
   int grp_in, grp_valid;          // rows per batch item in A / how many of them are real
   long long grp_stride, grp_off;  // output element offset = grp*grp_stride + grp_off + r*ldo
+  int tma_store;  // 1: epilogue stages rows in smem and writes with TMA (store / reduce-add); 0: per-thread stores
   const float* rope_cos;  // [rope_period, 32] or nullptr
   const float* rope_sin;
   int rope_cols;    // RoPE applies to output columns [0, rope_cols), 64-wide heads
@@ -49,8 +50,10 @@ struct GemmCfg {
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kEpiBufBytes = 4096;                  // 32 rows x 128 B, one TMA store box
+  static constexpr int kEpiBytes = 4 * 2 * kEpiBufBytes;     // 4 epilogue warps x double buffer
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;  // + alignment slack
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
@@ -68,11 +71,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                       const GemmParams p) {
+                       const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* bar_base = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint8_t* epi_base = smem + Cfg::kStages * Cfg::kStageBytes;   // 1024-aligned: stage sizes are multiples of 1024
+  uint8_t* bar_base = epi_base + Cfg::kEpiBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
@@ -89,6 +93,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (p.tma_store) tma_prefetch_desc(&map_out);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -165,6 +170,8 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;  // TMEM lane quarter this warp may read
+    uint8_t* my_bufs = epi_base + q * 2 * Cfg::kEpiBufBytes;
+    int buf_sel = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
@@ -226,7 +233,56 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             }
           }
         }
-        if (row_ok) {
+        if (p.tma_store) {
+          // Stage this warp's 32 rows in smem (128-byte rows, 16-byte chunks XOR-swizzled by row so
+          // the row-per-thread writes are bank-conflict free), then one TMA store / reduce-add per
+          // box: global writes are full 128-byte lines and the fp32 residual is never read back.
+          const int row0 = m_blk * GEMM_BM + q * 32;
+          const int sw = lane & 7;
+          if (p.out_mode == OUT_BF16) {
+            uint8_t* buf = my_bufs + buf_sel * Cfg::kEpiBufBytes;
+            if (lane == 0) tma_wait_group_read<1>();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint4 w;
+              w.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+              w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ sw) << 4)) = w;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_out, buf, n0, row0);
+              tma_commit_group();
+            }
+            buf_sel ^= 1;
+          } else {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              if (n0 + 32 * half < p.N) {  // uniform
+                uint8_t* buf = my_bufs + buf_sel * Cfg::kEpiBufBytes;
+                if (lane == 0) tma_wait_group_read<1>();
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float* vv = v + 32 * half + 4 * j;
+                  *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ sw) << 4)) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  if (p.out_mode == OUT_F32_RESIDUAL) tma_reduce_add_2d(&map_out, buf, n0 + 32 * half, row0);
+                  else tma_store_2d(&map_out, buf, n0 + 32 * half, row0);
+                  tma_commit_group();
+                }
+                buf_sel ^= 1;
+              }
+            }
+          }
+        } else if (row_ok) {
           if (p.out_mode == OUT_BF16) {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + n0;
 #pragma unroll
@@ -266,6 +322,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    if (p.tma_store && lane == 0) tma_wait_group<0>();  // all bulk stores of this thread have landed
   }
 
   __syncwarp();
