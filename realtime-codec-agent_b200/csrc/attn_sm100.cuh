@@ -31,7 +31,8 @@ inline bool attn_sm100_supported(int wl, int wr) { return wr == 0 && wl <= ATT_H
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_window_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                              __nv_bfloat16* __restrict__ out, int F, int H, int wl, float scale_log2e) {
+                              __nv_bfloat16* __restrict__ out, int F, int H, int wl, int out_rows,
+                              float scale_log2e) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -47,6 +48,8 @@ attention_window_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const _
   const int h = (blockIdx.x / q_tiles) % H;
   const int b = blockIdx.x / (q_tiles * H);
   const int d = H * 64;
+  const int first_out = F - out_rows;             // only queries >= first_out are stored (dead-output elimination)
+  if (q0 + ATT_BQ <= first_out) return;           // uniform: nothing of this tile is kept
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_q);
@@ -93,9 +96,12 @@ attention_window_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const _
   // key column c <-> key index kj = q0 - HALO + c; valid iff 0 <= kj < F and qi - wl <= kj <= qi
   const int c_lo = max(r + ATT_HALO - wl, ATT_HALO - q0);  // first valid column
   const int c_hi = (qi < F) ? (r + ATT_HALO) : -1;         // last valid column (causal); none for padded rows
+  // columns any row of this warp can attend: [32*warp + HALO - wl, 32*warp + HALO + 31]
+  const int wc_lo = warp * 32 + ATT_HALO - wl, wc_hi = warp * 32 + ATT_HALO + 31;
   float mx = -INFINITY;
 #pragma unroll 1
   for (int c0 = 0; c0 < ATT_NKV; c0 += 32) {
+    if (c0 + 31 < wc_lo || c0 > wc_hi) continue;  // warp-uniform: fully masked chunk
     uint32_t raw[32];
     tmem_ld_32x32b_x32(tmem_s + lane_addr + c0, raw);
     tmem_ld_wait();
@@ -109,6 +115,13 @@ attention_window_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const _
   float sum = 0.0f;
 #pragma unroll 1
   for (int c0 = 0; c0 < ATT_NKV; c0 += 32) {
+    uint8_t* atom = sP + (c0 >> 6) * (ATT_BQ * 128) + r * 128;
+    const int chunk0 = (c0 & 63) >> 3;
+    if (c0 + 31 < wc_lo || c0 > wc_hi) {          // fully masked for the whole warp: P = 0, no TMEM read
+#pragma unroll
+      for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(atom + (((chunk0 + u) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
     uint32_t raw[32];
     tmem_ld_32x32b_x32(tmem_s + lane_addr + c0, raw);
     tmem_ld_wait();
@@ -123,8 +136,6 @@ attention_window_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const _
       packed[j >> 1] = pack_bf16x2(p0, p1);
     }
     // 32 keys = 4 chunks of 16 bytes inside atom (c0 / 64), chunk index ((c0 % 64) / 8 + u) ^ (r & 7)
-    uint8_t* atom = sP + (c0 >> 6) * (ATT_BQ * 128) + r * 128;
-    const int chunk0 = (c0 & 63) >> 3;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int chunk = (chunk0 + u) ^ (r & 7);
@@ -157,9 +168,9 @@ attention_window_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const _
     tmem_ld_32x32b_x32(tmem_o + lane_addr, raw0);
     tmem_ld_32x32b_x32(tmem_o + lane_addr + 32, raw1);
     tmem_ld_wait();
-    if (qi < F) {
+    if (qi < F && qi >= first_out) {
       const float inv = 1.0f / sum;
-      __nv_bfloat16* o = out + (static_cast<long long>(b) * F + qi) * d + h * 64;
+      __nv_bfloat16* o = out + (static_cast<long long>(b) * out_rows + (qi - first_out)) * d + h * 64;
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         uint4 w;
@@ -188,7 +199,8 @@ attention_window_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const _
   }
 }
 
-inline int launch_attention_sm100(mc_handle* h, const bf16* qkv, bf16* out, int B, int F, cudaStream_t stream) {
+inline int launch_attention_sm100(mc_handle* h, const bf16* qkv, bf16* out, int B, int F, int out_rows,
+                                  cudaStream_t stream) {
   const mc_spec& s = h->spec;
   const int d = s.d_model;
   const CUtensorMap *mq, *mkv;
@@ -204,7 +216,7 @@ inline int launch_attention_sm100(mc_handle* h, const bf16* qkv, bf16* out, int 
   if (blocks > INT_MAX) return h->fail(MC_ERR_ARG, "attention: too many tiles");
   const dim3 grid((unsigned)blocks);
   attention_window_sm100_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(*mq, *mkv, out, F, s.n_heads, s.window_left,
-                                                                            0.125f * 1.4426950408889634f);
+                                                                            out_rows, 0.125f * 1.4426950408889634f);
   MC_LAUNCH_CHECK(h, "attention_window_sm100_kernel");
   return MC_OK;
 }

@@ -14,7 +14,7 @@ namespace mc {
 // scores, lanes <-> output dims for P*V.
 // ---------------------------------------------------------------------------------------------
 __global__ void attention_window_simt_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                                             int B, int F, int H, int wl, int wr, float scale) {
+                                             int B, int F, int H, int wl, int wr, int out_rows, float scale) {
   const int d = H * 64;
   const int lane = threadIdx.x & 31;
   const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
@@ -24,6 +24,8 @@ __global__ void attention_window_simt_kernel(const __nv_bfloat16* __restrict__ q
   const long long row = warp_global / H;
   const int i = static_cast<int>(row % F);
   const long long base_row = row - i;  // first row of this window
+  const int first_out = F - out_rows;
+  if (i < first_out) return;           // warp-uniform: this query is not kept
   const int j_lo = max(0, i - wl), j_hi = min(F - 1, i + wr);
   const int span = j_hi - j_lo + 1;
 
@@ -96,7 +98,8 @@ __global__ void attention_window_simt_kernel(const __nv_bfloat16* __restrict__ q
       }
     }
   }
-  *reinterpret_cast<uint32_t*>(out + row * d + h * 64 + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
+  const long long orow = (base_row / F) * out_rows + (i - first_out);
+  *reinterpret_cast<uint32_t*>(out + orow * d + h * 64 + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
 }
 
 // ---------------------------------------------------------------------------------------------

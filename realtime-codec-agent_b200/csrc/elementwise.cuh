@@ -94,6 +94,22 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// Keep the last r_out of r_in fp32 rows of every window (dead-output elimination between layers).
+// ---------------------------------------------------------------------------------------------
+__global__ void compact_rows_kernel(const float4* __restrict__ x, float4* __restrict__ y, int B, int r_in, int r_out,
+                                    int d4) {
+  const long long total = static_cast<long long>(B) * r_out * d4;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % d4);
+    const long long row = idx / d4;
+    const int j = static_cast<int>(row % r_out);
+    const long long b = row / r_out;
+    y[idx] = x[(b * r_in + (r_in - r_out) + j) * d4 + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Code embedding: codes int64 [M] -> bf16 [M, 64] = (projected codebook row, zero padded to the
 // 64-wide K block of the decoder's input projection).  One thread = one 16-byte store.
 // ---------------------------------------------------------------------------------------------

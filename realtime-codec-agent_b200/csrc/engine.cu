@@ -20,7 +20,7 @@ struct GemmCall {
   int M, N, K, act, out_mode;
   void* out; int64_t ldo;
   int grp_in = INT_MAX, grp_valid = INT_MAX; int64_t grp_stride = 0, grp_off = 0;
-  int rope_cols = 0, rope_period = 0;
+  int rope_cols = 0, rope_period = 0, rope_offset = 0;
   int block_n = 0;  // 0 = choose
 };
 
@@ -41,7 +41,7 @@ int launch_gemm_bn(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   p.M = c.M; p.N = c.N; p.K = c.K; p.a_k_wrap = c.a_k_wrap;
   p.bias = c.bias; p.act = c.act; p.out_mode = c.out_mode; p.out = c.out; p.ldo = c.ldo;
   p.grp_in = c.grp_in; p.grp_valid = c.grp_valid; p.grp_stride = c.grp_stride; p.grp_off = c.grp_off;
-  p.rope_cols = c.rope_cols; p.rope_period = c.rope_period;
+  p.rope_cols = c.rope_cols; p.rope_period = c.rope_period; p.rope_offset = c.rope_offset;
   p.rope_cos = c.rope_period > 0 ? h->ptr<float>("rope.cos") : nullptr;
   p.rope_sin = c.rope_period > 0 ? h->ptr<float>("rope.sin") : nullptr;
   static bool attr_set = false;
@@ -64,7 +64,7 @@ int launch_gemm(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   if (c.K % GEMM_BK != 0 || c.K % c.a_k_wrap != 0 || c.a_k_wrap % GEMM_BK != 0)
     return h->fail(MC_ERR_ARG, "gemm: K=%d a_k_wrap=%d must be multiples of %d", c.K, c.a_k_wrap, GEMM_BK);
   if (c.N % 8 != 0) return h->fail(MC_ERR_ARG, "gemm: N=%d must be a multiple of 8", c.N);
-  if (c.rope_period > 0 && c.rope_period > h->spec.max_positions)
+  if (c.rope_period > 0 && c.rope_period + c.rope_offset > h->spec.max_positions)
     return h->fail(MC_ERR_ARG, "gemm: rope period %d exceeds table rows %d", c.rope_period, h->spec.max_positions);
   int bn = c.block_n;
   if (bn == 0) {
@@ -101,12 +101,14 @@ int launch_rmsnorm(mc_handle* h, const float* x, const float* gamma, bf16* out, 
   return MC_OK;
 }
 
-int launch_attention(mc_handle* h, const bf16* qkv, bf16* out, int B, int F, int impl, cudaStream_t stream) {
+// qkv [B*F, 3d] -> out [B*out_rows, d]: only the last out_rows queries of each window are kept
+int launch_attention(mc_handle* h, const bf16* qkv, bf16* out, int B, int F, int out_rows, int impl, cudaStream_t stream) {
   const mc_spec& s = h->spec;
   const double span = std::min(F, s.window_left + s.window_right + 1);
-  McProfScope prof(h, 1, 4.0 * B * F * span * s.d_model, (double)B * F * s.d_model * 8.0, stream);
+  McProfScope prof(h, 1, 4.0 * B * out_rows * span * s.d_model,
+                   (double)B * (F * 2.0 + out_rows * 2.0) * s.d_model * 2.0, stream);
   if (impl == 0 && attn_sm100_supported(s.window_left, s.window_right)) {
-    MC_TRY(launch_attention_sm100(h, qkv, out, B, F, stream));
+    MC_TRY(launch_attention_sm100(h, qkv, out, B, F, out_rows, stream));
     return MC_OK;
   }
   if (s.window_left + s.window_right + 1 > 160) return h->fail(MC_ERR_ARG, "attention window too wide");
@@ -114,7 +116,7 @@ int launch_attention(mc_handle* h, const bf16* qkv, bf16* out, int B, int F, int
   const int threads = 256;
   const long long blocks = (warps * 32 + threads - 1) / threads;
   attention_window_simt_kernel<<<(unsigned)blocks, threads, 0, stream>>>(qkv, out, B, F, s.n_heads, s.window_left,
-                                                                         s.window_right, 0.125f);
+                                                                         s.window_right, out_rows, 0.125f);
   MC_LAUNCH_CHECK(h, "attention_window_simt_kernel");
   return MC_OK;
 }
@@ -122,51 +124,96 @@ int launch_attention(mc_handle* h, const bf16* qkv, bf16* out, int B, int F, int
 // ------------------------------------------------------- transformer stack
 struct StackBufs {
   float* x;   // [M,d] fp32 residual stream
+  float* x2;  // [M,d] second residual buffer (row compaction between layers ping-pongs x <-> x2)
   bf16* hbuf; // [M,d]
   bf16* qkv;  // [M,3d]
   bf16* att;  // [M,d]
   bf16* ffn;  // [M,f]
 };
 
-int run_layers(mc_handle* h, const char* prefix, int n_layers, const StackBufs& b, int B, int F, cudaStream_t stream) {
+// Runs n_layers blocks over B windows of F frames held in b.x and returns, in *x_out, the residual
+// stream restricted to the LAST keep_rows frames of every window ([B*keep_rows, d]).
+//
+// Dead-output elimination (exact): a layer whose output is needed only for the last R_out rows
+// needs keys/values for the last R_in = min(F, R_out + window_left) rows, so working backwards from
+// keep_rows each layer gets (R_in, R_out); rows outside are never computed.  Per-row arithmetic is
+// unchanged (same K order, same epilogues), so kept rows are bit-identical to the full pass.
+int run_layers(mc_handle* h, const char* prefix, int n_layers, const StackBufs& b, int B, int F, int keep_rows,
+               float** x_out, cudaStream_t stream) {
   const mc_spec& s = h->spec;
-  const int M = B * F, d = s.d_model, f = s.ffn_dim;
+  const int d = s.d_model, f = s.ffn_dim;
+  std::vector<int> r_in(n_layers), r_out(n_layers);
+  {
+    int need = std::max(1, std::min(keep_rows, F));
+    for (int l = n_layers - 1; l >= 0; --l) {
+      r_out[l] = need;
+      need = (need >= F) ? F : std::min(F, need + s.window_left);
+      r_in[l] = need;
+    }
+    if (n_layers > 0 && r_in[0] != F) {  // shallow stacks: the first layer still sees every row
+      r_in[0] = F;
+    }
+  }
+  float* x = b.x;
+  float* xalt = b.x2;
+  int rows = F;  // rows per window currently held in x
   char name[128];
   for (int l = 0; l < n_layers; ++l) {
     auto T = [&](const char* leaf) {
       snprintf(name, sizeof(name), "%s.layers.%d.%s", prefix, l, leaf);
       return std::string(name);
     };
-    MC_TRY(launch_rmsnorm(h, b.x, h->ptr<float>(T("norm1")), b.hbuf, M, d, INT_MAX, 0, 0, stream));
+    const int Ri = rows, Ro = std::min(r_out[l], rows);
+    const int Mi = B * Ri, Mo = B * Ro;
+    MC_TRY(launch_rmsnorm(h, x, h->ptr<float>(T("norm1")), b.hbuf, Mi, d, INT_MAX, 0, 0, stream));
     GemmCall g{};
-    g.A = b.hbuf; g.a_rows = M; g.a_k_wrap = d; g.W = h->ptr<bf16>(T("wqkv")); g.bias = h->ptr<float>(T("bqkv"));
-    g.M = M; g.N = 3 * d; g.K = d; g.act = ACT_NONE; g.out_mode = OUT_BF16; g.out = b.qkv; g.ldo = 3 * d;
-    g.rope_cols = 2 * d; g.rope_period = F;
+    g.A = b.hbuf; g.a_rows = Mi; g.a_k_wrap = d; g.W = h->ptr<bf16>(T("wqkv")); g.bias = h->ptr<float>(T("bqkv"));
+    g.M = Mi; g.N = 3 * d; g.K = d; g.act = ACT_NONE; g.out_mode = OUT_BF16; g.out = b.qkv; g.ldo = 3 * d;
+    g.rope_cols = 2 * d; g.rope_period = Ri; g.rope_offset = F - Ri;
     MC_TRY(launch_gemm(h, g, stream));
-    MC_TRY(launch_attention(h, b.qkv, b.att, B, F, h->attn_impl, stream));
+    MC_TRY(launch_attention(h, b.qkv, b.att, B, Ri, Ro, h->attn_impl, stream));
+    if (Ro < Ri) {
+      const long long items = (long long)Mo * (d / 4);
+      McProfScope prof(h, 3, 0.0, (double)Mo * d * 8.0, stream);
+      compact_rows_kernel<<<ew_grid(h, items, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(x),
+                                                                    reinterpret_cast<float4*>(xalt), B, Ri, Ro, d / 4);
+      MC_LAUNCH_CHECK(h, "compact_rows_kernel");
+      std::swap(x, xalt);
+      rows = Ro;
+    }
     GemmCall o{};
-    o.A = b.att; o.a_rows = M; o.a_k_wrap = d; o.W = h->ptr<bf16>(T("wo")); o.bias = h->ptr<float>(T("bo"));
-    o.M = M; o.N = d; o.K = d; o.act = ACT_NONE; o.out_mode = OUT_F32_RESIDUAL; o.out = b.x; o.ldo = d;
+    o.A = b.att; o.a_rows = Mo; o.a_k_wrap = d; o.W = h->ptr<bf16>(T("wo")); o.bias = h->ptr<float>(T("bo"));
+    o.M = Mo; o.N = d; o.K = d; o.act = ACT_NONE; o.out_mode = OUT_F32_RESIDUAL; o.out = x; o.ldo = d;
     MC_TRY(launch_gemm(h, o, stream));
-    MC_TRY(launch_rmsnorm(h, b.x, h->ptr<float>(T("norm2")), b.hbuf, M, d, INT_MAX, 0, 0, stream));
+    MC_TRY(launch_rmsnorm(h, x, h->ptr<float>(T("norm2")), b.hbuf, Mo, d, INT_MAX, 0, 0, stream));
     GemmCall u{};
-    u.A = b.hbuf; u.a_rows = M; u.a_k_wrap = d; u.W = h->ptr<bf16>(T("w1")); u.bias = h->ptr<float>(T("b1"));
-    u.M = M; u.N = f; u.K = d; u.act = ACT_GELU_TANH; u.out_mode = OUT_BF16; u.out = b.ffn; u.ldo = f;
+    u.A = b.hbuf; u.a_rows = Mo; u.a_k_wrap = d; u.W = h->ptr<bf16>(T("w1")); u.bias = h->ptr<float>(T("b1"));
+    u.M = Mo; u.N = f; u.K = d; u.act = ACT_GELU_TANH; u.out_mode = OUT_BF16; u.out = b.ffn; u.ldo = f;
     MC_TRY(launch_gemm(h, u, stream));
     GemmCall w{};
-    w.A = b.ffn; w.a_rows = M; w.a_k_wrap = f; w.W = h->ptr<bf16>(T("w2")); w.bias = h->ptr<float>(T("b2"));
-    w.M = M; w.N = d; w.K = f; w.act = ACT_NONE; w.out_mode = OUT_F32_RESIDUAL; w.out = b.x; w.ldo = d;
+    w.A = b.ffn; w.a_rows = Mo; w.a_k_wrap = f; w.W = h->ptr<bf16>(T("w2")); w.bias = h->ptr<float>(T("b2"));
+    w.M = Mo; w.N = d; w.K = f; w.act = ACT_NONE; w.out_mode = OUT_F32_RESIDUAL; w.out = x; w.ldo = d;
     MC_TRY(launch_gemm(h, w, stream));
   }
+  if (rows > keep_rows) {  // no layers (or window_left = 0 corner cases): compact at the end
+    const int Ro = keep_rows;
+    const long long items = (long long)B * Ro * (d / 4);
+    compact_rows_kernel<<<ew_grid(h, items, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(x),
+                                                                  reinterpret_cast<float4*>(xalt), B, rows, Ro, d / 4);
+    MC_LAUNCH_CHECK(h, "compact_rows_kernel");
+    std::swap(x, xalt);
+  }
+  *x_out = x;
   return MC_OK;
 }
 
 StackBufs carve_stack(Carver& cv, uint8_t* base, int M, int d, int f, bool dry) {
   StackBufs b{};
-  size_t ox = cv.take((size_t)M * d * 4), oh = cv.take((size_t)M * d * 2), oq = cv.take((size_t)M * 3 * d * 2),
-         oa = cv.take((size_t)M * d * 2), of = cv.take((size_t)M * f * 2);
+  size_t ox = cv.take((size_t)M * d * 4), ox2 = cv.take((size_t)M * d * 4), oh = cv.take((size_t)M * d * 2),
+         oq = cv.take((size_t)M * 3 * d * 2), oa = cv.take((size_t)M * d * 2), of = cv.take((size_t)M * f * 2);
   if (!dry) {
     b.x = reinterpret_cast<float*>(base + ox);
+    b.x2 = reinterpret_cast<float*>(base + ox2);
     b.hbuf = reinterpret_cast<bf16*>(base + oh);
     b.qkv = reinterpret_cast<bf16*>(base + oq);
     b.att = reinterpret_cast<bf16*>(base + oa);
@@ -255,16 +302,19 @@ int encode_impl(mc_handle* h, const float* wav, int64_t ld, int B, int T, int ke
     }
     MC_TRY(launch_gemm(h, g, stream));
   }
-  // ---- transformer
-  MC_TRY(run_layers(h, "enc", s.enc_layers, sb, B, F, stream));
-  MC_TRY(launch_rmsnorm(h, sb.x, h->ptr<float>("enc.norm_f"), sb.hbuf, M, d, INT_MAX, 0, 0, stream));
+  // ---- transformer (only the rows the kept frames depend on, unless the full latents are requested)
+  const int keep_rows = z_e_out ? F : keep;
+  float* xk = nullptr;
+  MC_TRY(run_layers(h, "enc", s.enc_layers, sb, B, F, keep_rows, &xk, stream));
+  const int Mk = B * keep_rows;
+  MC_TRY(launch_rmsnorm(h, xk, h->ptr<float>("enc.norm_f"), sb.hbuf, Mk, d, INT_MAX, 0, 0, stream));
   GemmCall pj{};
-  pj.A = sb.hbuf; pj.a_rows = M; pj.a_k_wrap = d; pj.W = h->ptr<bf16>("enc.proj.w"); pj.bias = h->ptr<float>("enc.proj.b");
-  pj.M = M; pj.N = dq; pj.K = d; pj.act = ACT_NONE; pj.out_mode = OUT_F32; pj.out = z_e; pj.ldo = dq;
+  pj.A = sb.hbuf; pj.a_rows = Mk; pj.a_k_wrap = d; pj.W = h->ptr<bf16>("enc.proj.w"); pj.bias = h->ptr<float>("enc.proj.b");
+  pj.M = Mk; pj.N = dq; pj.K = d; pj.act = ACT_NONE; pj.out_mode = OUT_F32; pj.out = z_e; pj.ldo = dq;
   MC_TRY(launch_gemm(h, pj, stream));
   if (z_e_out) MC_CUDA(h, cudaMemcpyAsync(z_e_out, z_e, (size_t)M * dq * 4, cudaMemcpyDeviceToDevice, stream));
-  // ---- quantise the kept frames
-  MC_TRY(launch_vq(h, z_e, B, F, keep, codes, margin, vq_scratch, stream));
+  // ---- quantise the kept frames (z_e holds keep_rows rows per window)
+  MC_TRY(launch_vq(h, z_e, B, keep_rows, keep, codes, margin, vq_scratch, stream));
   return MC_OK;
 }
 
@@ -290,7 +340,10 @@ int decode_impl(mc_handle* h, const int64_t* codes, const float* z_q, int B, int
     ds[i] = s.conv_strides[n - 1 - i];
     dch[i + 1] = (n - 2 - i >= 0) ? s.conv_channels[n - 2 - i] : 1;
   }
-  Tin[0] = F;
+  // Frames whose samples are kept, plus two more: the causal transposed convs look one step back at
+  // every rate, so a window cut at frame f0 has wrong samples only in its first 404 (< 2 frames).
+  const int Rk = (keep >= total) ? F : std::min(F, (keep + hop - 1) / hop + 2);
+  Tin[0] = Rk;
   for (int i = 1; i < n; ++i) Tin[i] = Tin[i - 1] * ds[i - 1];
 
   Carver cv;
@@ -317,14 +370,15 @@ int decode_impl(mc_handle* h, const int64_t* codes, const float* z_q, int B, int
   ip.A = a0; ip.a_rows = M; ip.a_k_wrap = 64; ip.W = h->ptr<bf16>("dec.in_proj.w"); ip.bias = h->ptr<float>("dec.in_proj.b");
   ip.M = M; ip.N = d; ip.K = 64; ip.act = ACT_NONE; ip.out_mode = OUT_F32; ip.out = sb.x; ip.ldo = d;
   MC_TRY(launch_gemm(h, ip, stream));
-  MC_TRY(run_layers(h, "dec", s.dec_layers, sb, B, F, stream));
+  float* xk = nullptr;
+  MC_TRY(run_layers(h, "dec", s.dec_layers, sb, B, F, Rk, &xk, stream));
 
   for (int i = 0; i < n; ++i) {  // zero row 0 (left pad) of every transposed-conv input
     const size_t pitch = (size_t)(1 + Tin[i]) * dch[i] * 2;
     MC_CUDA(h, cudaMemset2DAsync(base + tb_off[i], pitch, 0, (size_t)dch[i] * 2, B, stream));
   }
-  MC_TRY(launch_rmsnorm(h, sb.x, h->ptr<float>("dec.norm_f"), reinterpret_cast<bf16*>(base + tb_off[0]), M, d, F,
-                        (int64_t)(1 + F) * d, d, stream));
+  MC_TRY(launch_rmsnorm(h, xk, h->ptr<float>("dec.norm_f"), reinterpret_cast<bf16*>(base + tb_off[0]), B * Rk, d, Rk,
+                        (int64_t)(1 + Rk) * d, d, stream));
   for (int i = 0; i + 1 < n; ++i) {
     GemmCall g{};
     g.A = reinterpret_cast<const bf16*>(base + tb_off[i]);
@@ -554,7 +608,7 @@ int mc_op_rmsnorm(mc_handle* h, const float* x, const float* gamma, void* out_bf
 
 int mc_op_attention(mc_handle* h, const void* qkv, void* out, int32_t B, int32_t F, int32_t impl, mc_stream_t stream) {
   MC_ENTER(h);
-  return launch_attention(h, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, F, impl,
+  return launch_attention(h, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, F, F, impl,
                           (cudaStream_t)stream);
 }
 

@@ -36,7 +36,8 @@ struct GemmParams {
   const float* rope_cos;  // [rope_period, 32] or nullptr
   const float* rope_sin;
   int rope_cols;    // RoPE applies to output columns [0, rope_cols), 64-wide heads
-  int rope_period;  // position = (row within group) % rope_period
+  int rope_period;  // position = rope_offset + (row within group) % rope_period
+  int rope_offset;
 };
 
 constexpr int GEMM_BM = 128;
@@ -185,7 +186,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       const int r = g - grp * p.grp_in;
       const bool row_ok = (g < p.M) && (r < p.grp_valid);
       const long long obase = static_cast<long long>(grp) * p.grp_stride + p.grp_off + static_cast<long long>(r) * p.ldo;
-      const int pos = (p.rope_period > 0) ? (r % p.rope_period) : 0;
+      const int pos = (p.rope_period > 0) ? (p.rope_offset + r % p.rope_period) : 0;
 
 #pragma unroll 1
       for (int c = 0; c < BN / 64; ++c) {

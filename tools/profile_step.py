@@ -24,4 +24,8 @@ for it in range(2):
     print(f"iter {it}: {e0.elapsed_time(e1):.3f} ms for {B} windows; " +
           "; ".join(f"{k}: {v['ms']:.3f} ms / {v['launches']} launches" + (f" / {v['flops'] / v['ms'] / 1e9:.0f} TFLOP/s" if v['flops'] and v['ms'] else "")
                     for k, v in prof.items()))
-print("checksum", int(codes.sum()))
+print("checksum", int(codes.sum()), "audio_hash", float(wav.double().sum()), float(wav.double().abs().sum()))
+again = gen.encode(wav, keep_last_frames=5, row_stride=1600, num_windows=B, window_samples=32000)
+full = gen.encode(wav, keep_last_frames=0, row_stride=1600, num_windows=B, window_samples=32000)
+print("repeat_equal", bool(torch.equal(codes, again)), "full_vs_keep5_equal", bool(torch.equal(full[:, -5:], codes)),
+      "n_diff", int((full[:, -5:] != codes).sum()))
