@@ -60,6 +60,42 @@ int launch_gemm_bn(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   return MC_OK;
 }
 
+// CTA-pair kernel: 256 x 256 tiles on 74 clusters of two CTAs
+int launch_gemm_pair(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
+  constexpr int BN = 256;
+  const CUtensorMap *ma, *mb;
+  MC_TRY(get_map_2d_bf16(h, c.A, (uint64_t)c.a_k_wrap, (uint64_t)c.a_rows, GEMM_BK, GEMM_BM, &ma));
+  MC_TRY(get_map_2d_bf16(h, c.W, (uint64_t)c.K, (uint64_t)c.N, GEMM_BK, BN / 2, &mb));
+  const bool tma_out = (c.grp_in == INT_MAX);
+  const CUtensorMap* mo = ma;
+  if (tma_out) {
+    const int esize = c.out_mode == OUT_BF16 ? 2 : 4;
+    MC_TRY(get_map_2d(h, c.out, esize, (uint64_t)c.N, (uint64_t)c.M, (uint64_t)c.ldo * esize, esize == 2 ? 64 : 32, 32, &mo));
+  }
+  GemmParams p;
+  p.tma_store = tma_out ? 1 : 0;
+  p.M = c.M; p.N = c.N; p.K = c.K; p.a_k_wrap = c.a_k_wrap;
+  p.bias = c.bias; p.act = c.act; p.out_mode = c.out_mode; p.out = c.out; p.ldo = c.ldo;
+  p.grp_in = c.grp_in; p.grp_valid = c.grp_valid; p.grp_stride = c.grp_stride; p.grp_off = c.grp_off;
+  p.rope_cols = c.rope_cols; p.rope_period = c.rope_period; p.rope_offset = c.rope_offset;
+  p.rope_cos = c.rope_period > 0 ? h->ptr<float>("rope.cos") : nullptr;
+  p.rope_sin = c.rope_period > 0 ? h->ptr<float>("rope.sin") : nullptr;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MC_CUDA(h, cudaFuncSetAttribute(gemm2_bf16_sm100_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Gemm2Cfg<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  const int m_tiles = (c.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM), n_tiles = (c.N + BN - 1) / BN;
+  const int pairs = std::min(m_tiles * n_tiles, h->num_sms / 2);
+  const double valid_rows = c.grp_in == INT_MAX ? (double)c.M : (double)c.M / c.grp_in * c.grp_valid;
+  const double out_bytes = valid_rows * c.N * (c.out_mode == OUT_BF16 ? 2.0 : (c.out_mode == OUT_F32 ? 4.0 : 8.0));
+  McProfScope prof(h, 0, 2.0 * valid_rows * c.N * c.K, valid_rows * c.a_k_wrap * 2.0 + (double)c.N * c.K * 2.0 + out_bytes, stream);
+  gemm2_bf16_sm100_kernel<BN><<<2 * pairs, GEMM_THREADS, Gemm2Cfg<BN>::kSmemBytes, stream>>>(*ma, *mb, *mo, p);
+  MC_LAUNCH_CHECK(h, "gemm2_bf16_sm100_kernel");
+  return MC_OK;
+}
+
 int launch_gemm(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   if (c.K % GEMM_BK != 0 || c.K % c.a_k_wrap != 0 || c.a_k_wrap % GEMM_BK != 0)
     return h->fail(MC_ERR_ARG, "gemm: K=%d a_k_wrap=%d must be multiples of %d", c.K, c.a_k_wrap, GEMM_BK);
@@ -67,6 +103,11 @@ int launch_gemm(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   if (c.rope_period > 0 && c.rope_period + c.rope_offset > h->spec.max_positions)
     return h->fail(MC_ERR_ARG, "gemm: rope period %d exceeds table rows %d", c.rope_period, h->spec.max_positions);
   int bn = c.block_n;
+  {
+    // CTA pairs whenever there is at least one 256 x 256 tile per pair of SMs
+    const int m2 = (c.M + 255) / 256, n2 = (c.N + 255) / 256;
+    if ((bn == 0 && h->gemm_pair && c.N >= 256 && m2 * n2 >= h->num_sms / 2) || bn == 512) return launch_gemm_pair(h, c, stream);
+  }
   if (bn == 0) {
     const int m_tiles = (c.M + GEMM_BM - 1) / GEMM_BM;
     if (c.N >= 256 && m_tiles * ((c.N + 255) / 256) >= 2 * h->num_sms) bn = 256;
@@ -148,10 +189,11 @@ int run_layers(mc_handle* h, const char* prefix, int n_layers, const StackBufs& 
     for (int l = n_layers - 1; l >= 0; --l) {
       r_out[l] = need;
       need = (need >= F) ? F : std::min(F, need + s.window_left);
+      // Cut windows only at multiples of 16 frames: the P*V UMMA sums keys in groups of 16, and a cut
+      // that shifts a row's keys relative to those groups would change the summation order (results
+      // would still be correct but no longer bit-identical to the full-window pass).
+      if (need < F) need = F - ((F - need) / 16) * 16;
       r_in[l] = need;
-    }
-    if (n_layers > 0 && r_in[0] != F) {  // shallow stacks: the first layer still sees every row
-      r_in[0] = F;
     }
   }
   float* x = b.x;
@@ -580,6 +622,8 @@ int mc_profile_end(mc_handle* h, double* ms, double* flops, double* bytes, int64
 
 int mc_set_debug_impl(mc_handle* h, int32_t attention_impl, int32_t vq_impl) {
   if (!h) return MC_ERR_ARG;
+  h->gemm_pair = (attention_impl & 2) ? 0 : 1;   // bit 1: force the single-CTA GEMM (A/B measurements)
+  attention_impl &= 1;
   h->attn_impl = attention_impl;
   h->vq_impl = vq_impl;
   return MC_OK;

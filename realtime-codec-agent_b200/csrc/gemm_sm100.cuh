@@ -43,6 +43,7 @@ struct GemmParams {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 256;
+constexpr int kEpiBufBytes = 4096;  // 32 rows x 128 B: one TMA store box per epilogue warp and buffer
 
 template <int BN>
 struct GemmCfg {
@@ -51,7 +52,6 @@ struct GemmCfg {
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kEpiBufBytes = 4096;                  // 32 rows x 128 B, one TMA store box
   static constexpr int kEpiBytes = 4 * 2 * kEpiBufBytes;     // 4 epilogue warps x double buffer
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;  // + alignment slack
@@ -67,6 +67,152 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Drains one 128-row x BN accumulator slab: rows row_base + [0,128), columns n_base + [0,BN).
+// Called by the 4 epilogue warps (q = TMEM lane quarter); shared by the 1-CTA and 2-CTA kernels.
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_slab(const GemmParams& p, const CUtensorMap* map_out_p, uint32_t tmem_acc,
+                                                   int row_base, int n_base, int q, int lane, uint8_t* my_bufs,
+                                                   int& buf_sel) {
+      const int g = row_base + q * 32 + lane;  // A row handled by this thread
+      const int grp = g / p.grp_in;
+      const int r = g - grp * p.grp_in;
+      const bool row_ok = (g < p.M) && (r < p.grp_valid);
+      const long long obase = static_cast<long long>(grp) * p.grp_stride + p.grp_off + static_cast<long long>(r) * p.ldo;
+      const int pos = (p.rope_period > 0) ? (p.rope_offset + r % p.rope_period) : 0;
+
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        const int n0 = n_base + c * 64;
+        if (n0 >= p.N) break;  // uniform across the warp
+        uint32_t raw0[32], raw1[32];
+        const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c * 64;
+        tmem_ld_32x32b_x32(taddr, raw0);
+        tmem_ld_32x32b_x32(taddr + 32, raw1);
+        tmem_ld_wait();
+        float v[64];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = __uint_as_float(raw0[j]);
+          v[32 + j] = __uint_as_float(raw1[j]);
+        }
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            if (n0 + j < p.N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+        }
+        if (p.act == ACT_GELU_TANH) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = gelu_tanh_f(v[j]);
+        }
+        if (p.rope_cos != nullptr && n0 < p.rope_cols) {
+          // one 64-wide head per chunk: rotate (j, j+32) by the angle of (pos, j)
+          const float4* c4 = reinterpret_cast<const float4*>(p.rope_cos + static_cast<long long>(pos) * 32);
+          const float4* s4 = reinterpret_cast<const float4*>(p.rope_sin + static_cast<long long>(pos) * 32);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 cc = __ldg(c4 + (j >> 2));
+            const float4 ss = __ldg(s4 + (j >> 2));
+            const float cs[4] = {cc.x, cc.y, cc.z, cc.w};
+            const float sn[4] = {ss.x, ss.y, ss.z, ss.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float x1 = v[j + u], x2 = v[32 + j + u];
+              v[j + u] = x1 * cs[u] - x2 * sn[u];
+              v[32 + j + u] = x1 * sn[u] + x2 * cs[u];
+            }
+          }
+        }
+        if (p.tma_store) {
+          // Stage this warp's 32 rows in smem (128-byte rows, 16-byte chunks XOR-swizzled by row so
+          // the row-per-thread writes are bank-conflict free), then one TMA store / reduce-add per
+          // box: global writes are full 128-byte lines and the fp32 residual is never read back.
+          const int row0 = row_base + q * 32;
+          const int sw = lane & 7;
+          if (p.out_mode == OUT_BF16) {
+            uint8_t* buf = my_bufs + buf_sel * kEpiBufBytes;
+            if (lane == 0) tma_wait_group_read<1>();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint4 w;
+              w.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+              w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ sw) << 4)) = w;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(map_out_p, buf, n0, row0);
+              tma_commit_group();
+            }
+            buf_sel ^= 1;
+          } else {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              if (n0 + 32 * half < p.N) {  // uniform
+                uint8_t* buf = my_bufs + buf_sel * kEpiBufBytes;
+                if (lane == 0) tma_wait_group_read<1>();
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float* vv = v + 32 * half + 4 * j;
+                  *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ sw) << 4)) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  if (p.out_mode == OUT_F32_RESIDUAL) tma_reduce_add_2d(map_out_p, buf, n0 + 32 * half, row0);
+                  else tma_store_2d(map_out_p, buf, n0 + 32 * half, row0);
+                  tma_commit_group();
+                }
+                buf_sel ^= 1;
+              }
+            }
+          }
+        } else if (row_ok) {
+          if (p.out_mode == OUT_BF16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + n0;
+#pragma unroll
+            for (int j = 0; j < 64; j += 8) {
+              if (n0 + j < p.N) {
+                uint4 w;
+                w.x = pack_bf16x2(v[j], v[j + 1]);
+                w.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                w.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                w.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(o + j) = w;
+              }
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.out) + obase + n0;
+            if (p.out_mode == OUT_F32_RESIDUAL) {
+#pragma unroll
+              for (int j = 0; j < 64; j += 4) {
+                if (n0 + j < p.N) {
+                  float4 x = *reinterpret_cast<const float4*>(o + j);
+                  x.x += v[j]; x.y += v[j + 1]; x.z += v[j + 2]; x.w += v[j + 3];
+                  *reinterpret_cast<float4*>(o + j) = x;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 64; j += 4) {
+                if (n0 + j < p.N) {
+                  *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+              }
+            }
+          }
+        }
+      }
 }
 
 template <int BN>
@@ -171,7 +317,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;  // TMEM lane quarter this warp may read
-    uint8_t* my_bufs = epi_base + q * 2 * Cfg::kEpiBufBytes;
+    uint8_t* my_bufs = epi_base + q * 2 * kEpiBufBytes;
     int buf_sel = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -181,144 +327,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 
-      const int g = m_blk * GEMM_BM + q * 32 + lane;  // A row handled by this thread
-      const int grp = g / p.grp_in;
-      const int r = g - grp * p.grp_in;
-      const bool row_ok = (g < p.M) && (r < p.grp_valid);
-      const long long obase = static_cast<long long>(grp) * p.grp_stride + p.grp_off + static_cast<long long>(r) * p.ldo;
-      const int pos = (p.rope_period > 0) ? (p.rope_offset + r % p.rope_period) : 0;
-
-#pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
-        const int n0 = n_blk * BN + c * 64;
-        if (n0 >= p.N) break;  // uniform across the warp
-        uint32_t raw0[32], raw1[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 64;
-        tmem_ld_32x32b_x32(taddr, raw0);
-        tmem_ld_32x32b_x32(taddr + 32, raw1);
-        tmem_ld_wait();
-        float v[64];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = __uint_as_float(raw0[j]);
-          v[32 + j] = __uint_as_float(raw1[j]);
-        }
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 64; j += 4) {
-            if (n0 + j < p.N) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          }
-        }
-        if (p.act == ACT_GELU_TANH) {
-#pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = gelu_tanh_f(v[j]);
-        }
-        if (p.rope_cos != nullptr && n0 < p.rope_cols) {
-          // one 64-wide head per chunk: rotate (j, j+32) by the angle of (pos, j)
-          const float4* c4 = reinterpret_cast<const float4*>(p.rope_cos + static_cast<long long>(pos) * 32);
-          const float4* s4 = reinterpret_cast<const float4*>(p.rope_sin + static_cast<long long>(pos) * 32);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 cc = __ldg(c4 + (j >> 2));
-            const float4 ss = __ldg(s4 + (j >> 2));
-            const float cs[4] = {cc.x, cc.y, cc.z, cc.w};
-            const float sn[4] = {ss.x, ss.y, ss.z, ss.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float x1 = v[j + u], x2 = v[32 + j + u];
-              v[j + u] = x1 * cs[u] - x2 * sn[u];
-              v[32 + j + u] = x1 * sn[u] + x2 * cs[u];
-            }
-          }
-        }
-        if (p.tma_store) {
-          // Stage this warp's 32 rows in smem (128-byte rows, 16-byte chunks XOR-swizzled by row so
-          // the row-per-thread writes are bank-conflict free), then one TMA store / reduce-add per
-          // box: global writes are full 128-byte lines and the fp32 residual is never read back.
-          const int row0 = m_blk * GEMM_BM + q * 32;
-          const int sw = lane & 7;
-          if (p.out_mode == OUT_BF16) {
-            uint8_t* buf = my_bufs + buf_sel * Cfg::kEpiBufBytes;
-            if (lane == 0) tma_wait_group_read<1>();
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              uint4 w;
-              w.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
-              w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-              w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-              w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ sw) << 4)) = w;
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&map_out, buf, n0, row0);
-              tma_commit_group();
-            }
-            buf_sel ^= 1;
-          } else {
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              if (n0 + 32 * half < p.N) {  // uniform
-                uint8_t* buf = my_bufs + buf_sel * Cfg::kEpiBufBytes;
-                if (lane == 0) tma_wait_group_read<1>();
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float* vv = v + 32 * half + 4 * j;
-                  *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ sw) << 4)) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                  if (p.out_mode == OUT_F32_RESIDUAL) tma_reduce_add_2d(&map_out, buf, n0 + 32 * half, row0);
-                  else tma_store_2d(&map_out, buf, n0 + 32 * half, row0);
-                  tma_commit_group();
-                }
-                buf_sel ^= 1;
-              }
-            }
-          }
-        } else if (row_ok) {
-          if (p.out_mode == OUT_BF16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + n0;
-#pragma unroll
-            for (int j = 0; j < 64; j += 8) {
-              if (n0 + j < p.N) {
-                uint4 w;
-                w.x = pack_bf16x2(v[j], v[j + 1]);
-                w.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                w.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                w.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(o + j) = w;
-              }
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(p.out) + obase + n0;
-            if (p.out_mode == OUT_F32_RESIDUAL) {
-#pragma unroll
-              for (int j = 0; j < 64; j += 4) {
-                if (n0 + j < p.N) {
-                  float4 x = *reinterpret_cast<const float4*>(o + j);
-                  x.x += v[j]; x.y += v[j + 1]; x.z += v[j + 2]; x.w += v[j + 3];
-                  *reinterpret_cast<float4*>(o + j) = x;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 64; j += 4) {
-                if (n0 + j < p.N) {
-                  *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                }
-              }
-            }
-          }
-        }
-      }
+      gemm_epilogue_slab<BN>(p, &map_out, tmem_base + acc * BN, m_blk * GEMM_BM, n_blk * BN, q, lane, my_bufs, buf_sel);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -332,6 +341,159 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+
+// =============================================================================================
+// CTA-pair GEMM (tcgen05 cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN tile.
+// Each CTA loads its own 128 rows of A and HALF of the B tile (BN/2 weight rows); the leader's
+// single MMA thread issues 256 x BN x 16 UMMAs that read both CTAs' shared memory, and each CTA's
+// TMEM receives its own 128 accumulator rows.  Per 64-deep K block the pair moves 32+32 KiB for
+// 256x256x64 MACs — 1.5x the arithmetic intensity of the 128 x 256 single-CTA tile, which is what
+// the L2 -> SM path needs (the single-CTA kernel saturates L2 bandwidth near 1.0 PFLOP/s).
+//   full barrier   : leader's, count 2 (leader arrive.expect_tx for both CTAs' bytes + peer arrive)
+//   empty barrier  : per CTA, released by the leader's multicast tcgen05.commit
+//   tmem_full      : per CTA, multicast commit;  tmem_empty: leader's, 8 arrivals (4 warps x 2 CTAs)
+// =============================================================================================
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int kStageBytesA = GEMM_BM * GEMM_BK * 2;
+  static constexpr int kStageBytesB = (BN / 2) * GEMM_BK * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStages = 196608 / kStageBytes;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kEpiBytes = 4 * 2 * kEpiBufBytes;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                        const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
+  using Cfg = Gemm2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_base = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint8_t* bar_base = epi_base + Cfg::kEpiBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int m_tiles = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = p.K / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    if (p.tma_store) tma_prefetch_desc(&map_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 2);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_ptr, Cfg::kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kStageBytesA;
+          const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          else mbar_arrive_cluster(leader_full);
+          const int k_elem = kb * GEMM_BK;
+          const int row_off = k_elem / p.a_k_wrap;
+          const int a_k = k_elem - row_off * p.a_k_wrap;
+          tma_load_2d_pair(sa, &map_a, leader_full, a_k, m_blk * 2 * GEMM_BM + rank * GEMM_BM + row_off);
+          tma_load_2d_pair(sb, &map_b, leader_full, k_elem, n_blk * BN + rank * (BN / 2));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kStageBytesA;
+          const uint64_t adesc = umma_smem_desc_sw128(sa, 1024, 16);
+          const uint64_t bdesc = umma_smem_desc_sw128(sb, 1024, 16);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tmem_full[acc], 3);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    uint8_t* my_bufs = epi_base + q * 2 * kEpiBufBytes;
+    int buf_sel = 0;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      gemm_epilogue_slab<BN>(p, &map_out, tmem_base + acc * BN, m_blk * 2 * GEMM_BM + rank * GEMM_BM, n_blk * BN, q, lane,
+                             my_bufs, buf_sel);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+    }
+    if (p.tma_store && lane == 0) tma_wait_group<0>();
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's smem / barriers stay alive until the leader's last MMA and commit retired
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
   }
 }
 

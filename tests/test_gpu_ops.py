@@ -39,6 +39,29 @@ def test_gemm_fp32_out(gen, M, N, K, block_n):
     assert err < 2e-3, f"max abs err {err}"
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (300, 256, 128), (1000, 3072, 512), (2560, 512, 2048), (25600, 1024, 1024)])
+@pytest.mark.parametrize("mode", ["f32", "bf16_gelu", "residual"])
+def test_gemm_cta_pair_kernel(gen, M, N, K, mode):
+    """block_n=512 forces the cta_group::2 kernel (256 x 256 tiles on CTA pairs)."""
+    A = _rand((M, K), seed=21).to(torch.bfloat16)
+    W = (_rand((N, K), seed=22) / math.sqrt(K)).to(torch.bfloat16)
+    bias = _rand((N,), seed=23)
+    ref = A.float() @ W.float().t() + bias
+    if mode == "f32":
+        out = gen.op_gemm(A, W, bias=bias, out_mode=1, block_n=512)
+        tol = 2e-3
+    elif mode == "bf16_gelu":
+        out = gen.op_gemm(A, W, bias=bias, act=1, out_mode=0, block_n=512).float()
+        ref, tol = gelu_tanh(ref), 0.03
+    else:
+        x0 = _rand((M, N), seed=24)
+        out = x0.clone()
+        gen.op_gemm(A, W, bias=bias, out_mode=2, out=out, block_n=512)
+        ref, tol = x0 + ref, 2e-3
+    err = (out - ref).abs().max().item()
+    assert err < tol, f"max abs err {err}"
+
+
 @pytest.mark.parametrize("act", [0, 1])
 def test_gemm_bf16_out_bias_act(gen, act):
     M, N, K = 515, 1024, 512

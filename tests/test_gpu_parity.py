@@ -187,8 +187,14 @@ def test_default_spec_shapes_and_determinism():
     assert torch.equal(codes, gen.encode(wav, row_stride=1600, num_windows=64, window_samples=32000, keep_last_frames=5))
     one = gen.encode(wav[1600 * 7: 1600 * 7 + 32000][None], keep_last_frames=5)
     assert torch.equal(one[0], codes[7])
+    # dead-output elimination is exact: asking for the last 5 frames == slicing the full pass
+    full = gen.encode(wav, row_stride=1600, num_windows=64, window_samples=32000)
+    assert torch.equal(full[:, -5:], codes)
     rec = gen.decode(codes.reshape(2, 160))
     assert rec.shape == (2, 160 * 320) and torch.isfinite(rec).all()
+    ctx = full[:8]                                              # 8 windows x 100 codes
+    assert torch.equal(gen.decode(ctx, keep_last_samples=1920), gen.decode(ctx)[:, -1920:])
+    assert torch.equal(gen.decode(ctx, keep_last_samples=320), gen.decode(ctx)[:, -320:])
     tok = pkg.AudioTokenizer(codec_model=gen, device="cuda")
     assert tok.framerate == 50.0
     assert len(tok.tokenize_audio(wav[:1600].cpu().numpy())) == 5

@@ -44,11 +44,17 @@ def diag_gemm():
         out = gen.op_gemm(A, W, out_mode=1, block_n=bn)
         torch.cuda.synchronize()
         summarize(f"gemm M{M} N{N} K{K} bn{bn}", out, A.float() @ W.float().t())
+    for (M, N, K) in [(256, 256, 64), (256, 256, 256), (300, 512, 128), (25600, 1024, 1024)]:
+        A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+        W = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
+        out = gen.op_gemm(A, W, out_mode=1, block_n=512)
+        torch.cuda.synchronize()
+        summarize(f"PAIR gemm M{M} N{N} K{K}", out, A.float() @ W.float().t())
     # timing of the big one
     A = torch.randn(25600, 1024, device="cuda").to(torch.bfloat16)
     W = (torch.randn(4096, 1024, device="cuda") / 32).to(torch.bfloat16)
     out = torch.empty(25600, 4096, device="cuda", dtype=torch.bfloat16)
-    for bn in (128, 256):
+    for bn in (128, 256, 512):
         for _ in range(3):
             gen.op_gemm(A, W, out_mode=0, out=out, block_n=bn)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
