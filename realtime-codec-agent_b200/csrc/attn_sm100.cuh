@@ -199,6 +199,266 @@ attention_window_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const _
   }
 }
 
+// =============================================================================================
+// v2: persistent, two-slot pipelined version of the same computation.  One CTA per SM walks the
+// (window, head, query-tile) items; while the four softmax warps work on item i in slot i&1, the
+// TMA warp is already loading item i+1 into the other slot and the MMA warp has issued its S=QK^T.
+//   warp 0  TMA producer      kv_full[s]   (tx)      <- slot_free[s]
+//   warp 1  MMA issuer        s_full[s], o_full[s]   <- kv_full[s], p_full[s]
+//   warps 2-5 / 6-9  softmax+output of slot 0 / slot 1:  p_full[s], slot_free[s] <- s_full[s], o_full[s]
+// The two softmax groups ping-pong: while one waits for its P*V to retire, the other is in its
+// softmax.  Each softmax thread needs only the 64 score columns its row can see (32q .. 32q+63),
+// read once from TMEM.  Masking is branch-free (masked scores become -inf, exp2 gives 0) and the row
+// sum is accumulated strictly in ascending key order so that results do not depend on where the
+// window was cut for dead-output elimination (adding the exact zeros of masked keys is a no-op).
+// =============================================================================================
+constexpr int ATT2_THREADS = 320;
+constexpr int ATT2_SLOT_BYTES = ATT_SMEM_Q + 2 * ATT_SMEM_KV + ATT_SMEM_P;   // 106496
+constexpr int ATT2_SMEM_BYTES = 2 * ATT2_SLOT_BYTES + 256 + 1024;
+constexpr int ATT2_TMEM_COLS = 512;
+
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+attention_window_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                                 __nv_bfloat16* __restrict__ out, int B, int F, int H, int wl, int out_rows,
+                                 float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * ATT2_SLOT_BYTES);
+  uint64_t* kv_full = bars;        // [2]
+  uint64_t* s_full = bars + 2;     // [2]
+  uint64_t* p_full = bars + 4;     // [2]
+  uint64_t* o_full = bars + 6;     // [2]
+  uint64_t* slot_free = bars + 8;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = H * 64;
+  const int first_out = F - out_rows;
+  const int q_tiles = (F + ATT_BQ - 1) / ATT_BQ;
+  const int first_tile = first_out / ATT_BQ;          // query tiles before it hold no kept row
+  const int kept_tiles = q_tiles - first_tile;
+  const int n_items = B * H * kept_tiles;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_kv);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 4);
+      mbar_init(&o_full[s], 1);
+      mbar_init(&slot_free[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, ATT2_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint32_t use = (it >> 1) & 1;
+        const int qt = first_tile + item % kept_tiles;
+        const int h = (item / kept_tiles) % H;
+        const int b = item / (kept_tiles * H);
+        uint8_t* slot = smem + s * ATT2_SLOT_BYTES;
+        mbar_wait(&slot_free[s], use ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], ATT_SMEM_Q + 2 * ATT_SMEM_KV);
+        const int row_q = b * F + qt * ATT_BQ;
+        tma_load_2d(slot, &map_q, &kv_full[s], h * 64, row_q);
+        tma_load_2d(slot + ATT_SMEM_Q, &map_kv, &kv_full[s], d + h * 64, row_q - ATT_HALO);
+        tma_load_2d(slot + ATT_SMEM_Q + ATT_SMEM_KV, &map_kv, &kv_full[s], 2 * d + h * 64, row_q - ATT_HALO);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, ATT_NKV, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, 64, 0, 1);
+      const int my_items = (n_items > static_cast<int>(blockIdx.x)) ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      // Each slot alternates  S(it) -> P*V(it) -> S(it+2) -> ...; the two slots progress independently,
+      // so the single issuing thread polls both and issues whatever is ready.
+      int cur[2] = {0, 1};
+      bool need_pv[2] = {false, false};
+      int remaining = 2 * my_items;  // MMA groups still to issue
+      const long long t0 = clock64();
+      while (remaining > 0) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (cur[s] >= my_items) continue;
+          const uint32_t use = (cur[s] >> 1) & 1;
+          uint8_t* slot = smem + s * ATT2_SLOT_BYTES;
+          if (!need_pv[s]) {
+            if (!mbar_try_wait(&kv_full[s], use)) continue;
+            tc_fence_after();
+            const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(slot), 1024, 16);
+            const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(slot + ATT_SMEM_Q), 1024, 16);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + s * 256, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+            umma_commit(&s_full[s]);
+            need_pv[s] = true;
+            --remaining;
+          } else {
+            if (!mbar_try_wait(&p_full[s], use)) continue;
+            tc_fence_after();
+            uint8_t* sV = slot + ATT_SMEM_Q + ATT_SMEM_KV;
+            uint8_t* sP = sV + ATT_SMEM_KV;
+#pragma unroll
+            for (int k = 0; k < ATT_NKV / 16; ++k) {
+              const uint64_t pdesc = umma_smem_desc_sw128(smem_u32(sP + (k >> 2) * (ATT_BQ * 128)) + (k & 3) * 32, 1024, 16);
+              const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sV) + k * 2048, 1024, 1024);
+              umma_bf16_ss(tmem_base + s * 256 + ATT_NKV, pdesc, vdesc, idesc_o, k != 0);
+            }
+            umma_commit(&o_full[s]);
+            need_pv[s] = false;
+            cur[s] += 2;
+            --remaining;
+          }
+        }
+        if (clock64() - t0 > 8000000000LL) {
+          printf("attention v2: MMA issuer timeout, block %d\n", blockIdx.x);
+          __trap();
+        }
+      }
+    }
+  } else {
+    const int group = (warp - 2) >> 2;         // softmax group = slot it serves
+    const int q = warp & 3;                    // TMEM lane quarter
+    const int r = q * 32 + lane;               // query row inside the tile
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const int s = group;
+    uint8_t* slot = smem + s * ATT2_SLOT_BYTES;
+    uint8_t* sP = slot + ATT_SMEM_Q + 2 * ATT_SMEM_KV;
+    const uint32_t tmem_s = tmem_base + s * 256;
+    const uint32_t tmem_o = tmem_s + ATT_NKV;
+    for (int it = group; blockIdx.x + static_cast<long long>(it) * gridDim.x < n_items; it += 2) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const uint32_t use = (it >> 1) & 1;
+      const int qt = first_tile + item % kept_tiles;
+      const int h = (item / kept_tiles) % H;
+      const int b = item / (kept_tiles * H);
+      const int q0 = qt * ATT_BQ;
+      const int qi = q0 + r;
+
+      mbar_wait(&s_full[s], use);
+      tc_fence_after();
+      // this warp's rows see key columns 32q + HALO - wl .. 32q + HALO + 31, all inside [32q, 32q + 64)
+      uint32_t raw0[32], raw1[32];
+      tmem_ld_32x32b_x32(tmem_s + lane_addr + q * 32, raw0);
+      tmem_ld_32x32b_x32(tmem_s + lane_addr + q * 32 + 32, raw1);
+      tmem_ld_wait();
+      const int c_lo = max(r + ATT_HALO - wl, ATT_HALO - q0) - q * 32;   // relative to column 32q
+      const int c_hi = (qi < F) ? (r + ATT_HALO - q * 32) : -1;
+      float sc[64];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        sc[j] = (j >= c_lo && j <= c_hi) ? __uint_as_float(raw0[j]) * scale_log2e : -INFINITY;
+        sc[32 + j] = (j + 32 >= c_lo && j + 32 <= c_hi) ? __uint_as_float(raw1[j]) * scale_log2e : -INFINITY;
+      }
+#pragma unroll
+      for (int j = 0; j < 64; ++j) mx = fmaxf(mx, sc[j]);
+      const float mref = (mx == -INFINITY) ? 0.0f : mx;
+      float sum = 0.0f;
+      uint32_t pk[32];
+#pragma unroll
+      for (int j = 0; j < 64; j += 2) {   // ascending keys, one accumulator
+        float p0, p1;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(sc[j] - mref));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(sc[j + 1] - mref));
+        sum += p0 + p1;
+        pk[j >> 1] = pack_bf16x2(p0, p1);
+      }
+      // P row (160 keys = 20 chunks of 16 B over three 64-key atoms): two live 32-key chunks, zeros elsewhere
+#pragma unroll
+      for (int c0 = 0; c0 < ATT_NKV; c0 += 32) {
+        uint8_t* atom = sP + (c0 >> 6) * (ATT_BQ * 128) + r * 128;
+        const int chunk0 = (c0 & 63) >> 3;
+        const int rel = (c0 >> 5) - q;  // 0 -> first live chunk, 1 -> second, else zero
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 w = make_uint4(0, 0, 0, 0);
+          if (rel == 0) w = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+          else if (rel == 1) w = make_uint4(pk[16 + 4 * u], pk[16 + 4 * u + 1], pk[16 + 4 * u + 2], pk[16 + 4 * u + 3]);
+          *reinterpret_cast<uint4*>(atom + (((chunk0 + u) ^ (r & 7)) << 4)) = w;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[s]);
+
+      mbar_wait(&o_full[s], use);
+      tc_fence_after();
+      tmem_ld_32x32b_x32(tmem_o + lane_addr, raw0);
+      tmem_ld_32x32b_x32(tmem_o + lane_addr + 32, raw1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slot_free[s]);   // TMEM and smem of this slot may be refilled
+      if (qi < F && qi >= first_out) {
+        const float inv = 1.0f / sum;
+        __nv_bfloat16* o = out + (static_cast<long long>(b) * out_rows + (qi - first_out)) * d + h * 64;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(raw0[j]) * inv, __uint_as_float(raw0[j + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(raw0[j + 2]) * inv, __uint_as_float(raw0[j + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(raw0[j + 4]) * inv, __uint_as_float(raw0[j + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(raw0[j + 6]) * inv, __uint_as_float(raw0[j + 7]) * inv);
+          *reinterpret_cast<uint4*>(o + j) = w;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(raw1[j]) * inv, __uint_as_float(raw1[j + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(raw1[j + 2]) * inv, __uint_as_float(raw1[j + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(raw1[j + 4]) * inv, __uint_as_float(raw1[j + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(raw1[j + 6]) * inv, __uint_as_float(raw1[j + 7]) * inv);
+          *reinterpret_cast<uint4*>(o + 32 + j) = w;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ATT2_TMEM_COLS);
+  }
+}
+
+inline int launch_attention_sm100_v2(mc_handle* h, const bf16* qkv, bf16* out, int B, int F, int out_rows,
+                                     cudaStream_t stream) {
+  const mc_spec& s = h->spec;
+  const int d = s.d_model;
+  const CUtensorMap *mq, *mkv;
+  MC_TRY(mc_internal::get_map_2d_bf16(h, qkv, (uint64_t)3 * d, (uint64_t)B * F, 64, ATT_BQ, &mq));
+  MC_TRY(mc_internal::get_map_2d_bf16(h, qkv, (uint64_t)3 * d, (uint64_t)B * F, 64, ATT_NKV, &mkv));
+  static bool attr_set = false;
+  if (!attr_set) {
+    MC_CUDA(h, cudaFuncSetAttribute(attention_window_sm100_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    ATT2_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int q_tiles = (F + ATT_BQ - 1) / ATT_BQ;
+  const long long items = (long long)B * s.n_heads * (q_tiles - (F - out_rows) / ATT_BQ);
+  if (items > INT_MAX) return h->fail(MC_ERR_ARG, "attention: too many tiles");
+  const int grid = (int)std::min<long long>(items, h->num_sms);
+  attention_window_sm100_v2_kernel<<<grid, ATT2_THREADS, ATT2_SMEM_BYTES, stream>>>(
+      *mq, *mkv, out, B, F, s.n_heads, s.window_left, out_rows, 0.125f * 1.4426950408889634f);
+  MC_LAUNCH_CHECK(h, "attention_window_sm100_v2_kernel");
+  return MC_OK;
+}
+
 inline int launch_attention_sm100(mc_handle* h, const bf16* qkv, bf16* out, int B, int F, int out_rows,
                                   cudaStream_t stream) {
   const mc_spec& s = h->spec;

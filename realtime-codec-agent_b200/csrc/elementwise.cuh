@@ -13,39 +13,42 @@ namespace mc {
 // One thread = one output frame x 8 channels (one 16-byte store).  Samples >= T read as zero
 // (this IS pad_audio: right padding to the hop multiple, audio_tokenizer.py:190).
 // ---------------------------------------------------------------------------------------------
-template <int MAXK>
-__global__ void conv_first_kernel(const float* __restrict__ wav, long long ld, int T, int B, int T0, int s0, int C0,
-                                  const float* __restrict__ w /*[2*s0, C0]*/, const float* __restrict__ bias,
-                                  __nv_bfloat16* __restrict__ out, int pad_rows) {
-  extern __shared__ float sw[];  // [2*s0*C0] weights + [C0] bias
-  const int k = 2 * s0;
-  for (int i = threadIdx.x; i < k * C0; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < C0; i += blockDim.x) sw[k * C0 + i] = bias[i];
-  __syncthreads();
+template <int KT>  // taps = 2 * stride
+__global__ void __launch_bounds__(256)
+conv_first_kernel(const float* __restrict__ wav, long long ld, int T, int B, int T0, int s0, int C0,
+                  const float* __restrict__ w /*[KT, C0]*/, const float* __restrict__ bias,
+                  __nv_bfloat16* __restrict__ out, int pad_rows) {
+  // A thread keeps ONE group of 8 output channels for its whole life: its KT x 8 weights and 8 biases
+  // live in registers, so the inner loop has no shared-memory traffic at all.
   const int cgroups = C0 / 8;
-  const long long total = static_cast<long long>(B) * T0 * cgroups;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(idx % cgroups);
-    const long long bt = idx / cgroups;
+  const int cg = threadIdx.x % cgroups;
+  const int slot = threadIdx.x / cgroups;
+  const int frames_per_block = blockDim.x / cgroups;
+  float wr[KT][8], br[8];
+#pragma unroll
+  for (int j = 0; j < KT; ++j) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w + j * C0 + cg * 8));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(w + j * C0 + cg * 8 + 4));
+    wr[j][0] = a.x; wr[j][1] = a.y; wr[j][2] = a.z; wr[j][3] = a.w;
+    wr[j][4] = c.x; wr[j][5] = c.y; wr[j][6] = c.z; wr[j][7] = c.w;
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) br[c] = __ldg(bias + cg * 8 + c);
+  const long long total = static_cast<long long>(B) * T0;
+  for (long long bt = blockIdx.x * static_cast<long long>(frames_per_block) + slot; bt < total;
+       bt += static_cast<long long>(gridDim.x) * frames_per_block) {
     const int t = static_cast<int>(bt % T0);
     const int b = static_cast<int>(bt / T0);
     const float* x = wav + b * ld;
-    float xin[MAXK];
-#pragma unroll
-    for (int j = 0; j < MAXK; ++j) {
-      const int n = t * s0 + j - s0;
-      xin[j] = (j < k && n >= 0 && n < T) ? __ldg(x + n) : 0.0f;
-    }
     float acc[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = sw[k * C0 + cg * 8 + c];
+    for (int c = 0; c < 8; ++c) acc[c] = br[c];
 #pragma unroll
-    for (int j = 0; j < MAXK; ++j) {
-      if (j < k) {
+    for (int j = 0; j < KT; ++j) {
+      const int n = t * s0 + j - s0;
+      const float xv = (n >= 0 && n < T) ? __ldg(x + n) : 0.0f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = fmaf(xin[j], sw[j * C0 + cg * 8 + c], acc[c]);
-      }
+      for (int c = 0; c < 8; ++c) acc[c] = fmaf(xv, wr[j][c], acc[c]);
     }
     uint4 o;
     o.x = pack_bf16x2(gelu_tanh_f(acc[0]), gelu_tanh_f(acc[1]));

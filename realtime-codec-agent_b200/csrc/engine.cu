@@ -149,6 +149,10 @@ int launch_attention(mc_handle* h, const bf16* qkv, bf16* out, int B, int F, int
   McProfScope prof(h, 1, 4.0 * B * out_rows * span * s.d_model,
                    (double)B * (F * 2.0 + out_rows * 2.0) * s.d_model * 2.0, stream);
   if (impl == 0 && attn_sm100_supported(s.window_left, s.window_right)) {
+    MC_TRY(launch_attention_sm100_v2(h, qkv, out, B, F, out_rows, stream));
+    return MC_OK;
+  }
+  if (impl == 2 && attn_sm100_supported(s.window_left, s.window_right)) {   // one-item-per-CTA version (A/B timing)
     MC_TRY(launch_attention_sm100(h, qkv, out, B, F, out_rows, stream));
     return MC_OK;
   }
@@ -314,14 +318,20 @@ int encode_impl(mc_handle* h, const float* wav, int64_t ld, int B, int T, int ke
   }
   {
     const int s0 = s.conv_strides[0], C0 = Cl[0];
-    if (2 * s0 > 16 || C0 % 8 != 0) return h->fail(MC_ERR_ARG, "conv0: stride %d / channels %d unsupported", s0, C0);
-    const long long items = (long long)B * Tl[0] * (C0 / 8);
+    const int cgroups = C0 / 8;
+    if ((2 * s0 != 8 && 2 * s0 != 16) || C0 % 8 != 0 || 256 % cgroups != 0)
+      return h->fail(MC_ERR_ARG, "conv0: stride %d / channels %d unsupported", s0, C0);
     const int threads = 256;
-    const size_t smem = (size_t)(2 * s0 * C0 + C0) * 4;
+    const long long frames = (long long)B * Tl[0];
+    const int grid = ew_grid(h, frames * cgroups, threads);
     McProfScope prof(h, 3, 2.0 * B * Tl[0] * 2 * s0 * C0, (double)B * T * 4.0 + (double)B * Tl[0] * C0 * 2.0, stream);
-    conv_first_kernel<16><<<ew_grid(h, items, threads), threads, smem, stream>>>(
-        wav, ld, T, B, Tl[0], s0, C0, h->ptr<float>("enc.conv0.w"), h->ptr<float>("enc.conv0.b"),
-        reinterpret_cast<bf16*>(base + conv_off[0]), s.conv_strides[1]);
+    bf16* o0 = reinterpret_cast<bf16*>(base + conv_off[0]);
+    if (2 * s0 == 8)
+      conv_first_kernel<8><<<grid, threads, 0, stream>>>(wav, ld, T, B, Tl[0], s0, C0, h->ptr<float>("enc.conv0.w"),
+                                                          h->ptr<float>("enc.conv0.b"), o0, s.conv_strides[1]);
+    else
+      conv_first_kernel<16><<<grid, threads, 0, stream>>>(wav, ld, T, B, Tl[0], s0, C0, h->ptr<float>("enc.conv0.w"),
+                                                           h->ptr<float>("enc.conv0.b"), o0, s.conv_strides[1]);
     MC_LAUNCH_CHECK(h, "conv_first_kernel");
   }
   for (int i = 1; i < n; ++i) {
@@ -622,8 +632,8 @@ int mc_profile_end(mc_handle* h, double* ms, double* flops, double* bytes, int64
 
 int mc_set_debug_impl(mc_handle* h, int32_t attention_impl, int32_t vq_impl) {
   if (!h) return MC_ERR_ARG;
-  h->gemm_pair = (attention_impl & 2) ? 0 : 1;   // bit 1: force the single-CTA GEMM (A/B measurements)
-  attention_impl &= 1;
+  h->gemm_pair = (attention_impl & 4) ? 0 : 1;   // bit 2: force the single-CTA GEMM (A/B measurements)
+  attention_impl &= 3;
   h->attn_impl = attention_impl;
   h->vq_impl = vq_impl;
   return MC_OK;

@@ -131,8 +131,8 @@ def test_rmsnorm(gen):
     assert (out.float() - ref).abs().max().item() < 0.03
 
 
-@pytest.mark.parametrize("impl", [0, 1])
-@pytest.mark.parametrize("B,Fr", [(1, 100), (3, 100), (2, 37), (1, 128), (2, 300)])
+@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("B,Fr", [(1, 100), (3, 100), (2, 37), (1, 128), (2, 300), (40, 100)])
 def test_window_attention(gen, impl, B, Fr):
     d, H = gen.spec.d_model, gen.spec.n_heads
     qkv = _rand((B * Fr, 3 * d), seed=18).to(torch.bfloat16)
