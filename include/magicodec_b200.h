@@ -98,6 +98,22 @@ int mc_vq_search(mc_handle* h, const float* z, int32_t M, int64_t* codes, float*
 /* Copies the cached projected codebook, fp32 [K, dq]. */
 int mc_codebook(mc_handle* h, float* out, mc_stream_t stream);
 
+/* ---- streaming sessions: the rolling context of tokenize_audio / detokenize_audio
+ * (audio_tokenizer.py:72-74, 111-113) resident in HBM; the steady state is one CUDA-graph launch per
+ * call.  chunk / codes / outputs are HOST pointers (staged through pinned memory); these calls
+ * synchronise `stream` before returning because the caller consumes the result. */
+typedef struct mc_stream mc_stream;
+int mc_stream_create(mc_handle* h, int32_t channels, int32_t context_samples, int32_t max_chunk_samples, mc_stream** out);
+int mc_stream_destroy(mc_stream* s);
+int mc_stream_reset(mc_stream* s);                      /* AudioTokenizer.reset_context, :44-46 */
+/* chunk fp32 [C,n]; codes_out int64 [C,keep_frames] (0 = every frame of the window). */
+int mc_stream_push_audio(mc_stream* s, const float* chunk, int32_t n, int32_t keep_frames, int64_t* codes_out,
+                         int32_t* frames_out, mc_stream_t stream);
+/* codes int64 [C,n]; wav_out fp32 [C,keep_samples] (0 = the whole decoded window). */
+int mc_stream_push_codes(mc_stream* s, const int64_t* codes, int32_t n, int32_t keep_samples, float* wav_out,
+                         int32_t* samples_out, mc_stream_t stream);
+int mc_stream_set_graphs(mc_stream* s, int32_t enabled); /* 0: direct launches (A/B timing, debugging) */
+
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t mc_launch_count(const mc_handle* h);
 /* Device timing by kernel class (0 GEMM, 1 attention, 2 VQ search, 3 HBM-bound elementwise): between

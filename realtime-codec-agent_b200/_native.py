@@ -49,6 +49,12 @@ SYMBOLS = {
     "mc_set_debug_impl": (C.c_int, [_P, _I32, _I32]),
     "mc_profile_begin": (C.c_int, [_P]),
     "mc_profile_end": (C.c_int, [_P, _P, _P, _P, _P, _I32]),
+    "mc_stream_create": (C.c_int, [_P, _I32, _I32, _I32, C.POINTER(_P)]),
+    "mc_stream_destroy": (C.c_int, [_P]),
+    "mc_stream_reset": (C.c_int, [_P]),
+    "mc_stream_push_audio": (C.c_int, [_P, _P, _I32, _I32, _P, C.POINTER(_I32), _P]),
+    "mc_stream_push_codes": (C.c_int, [_P, _P, _I32, _I32, _P, C.POINTER(_I32), _P]),
+    "mc_stream_set_graphs": (C.c_int, [_P, _I32]),
     "mc_op_gemm": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _I64,
                              _I32, _I32, _I64, _I64, _I32, _I32, _I32, _P]),
     "mc_op_rmsnorm": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P]),

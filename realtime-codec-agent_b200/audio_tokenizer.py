@@ -80,12 +80,24 @@ class AudioTokenizer:
         self.framerate = self._compute_framerate()
         self.context_samples = int(self.context_secs * self.sampling_rate)
         self.context_frames = int(self.context_secs * self.framerate * self.num_channels)
+        self._session = None
         self.reset_context()
 
     # ------------------------------------------------------------------ state
     def reset_context(self):
         self.tokenize_context = np.zeros((self.num_channels, 0), dtype=np.float32)
         self.detokenize_context = ""
+        if getattr(self, "_session", None) is not None:
+            self._session.reset()
+        self._session_audio_ok = self._session_codes_ok = True      # device context mirrors the host context
+
+    def _stream_session(self):
+        """Device-resident twin of the two contexts (native engine only), created on first use."""
+        if self._session is None:
+            self._session = self.codec_model.open_stream(self.num_channels, self.context_samples)
+            self._session_audio_ok = self.tokenize_context.shape[-1] == 0
+            self._session_codes_ok = len(self.detokenize_context) == 0
+        return self._session
 
     def get_audio_codes_str_secs(self, audio_codes_str: str) -> float:
         return len(audio_codes_str) / (self.framerate * self.num_channels)
@@ -110,10 +122,21 @@ class AudioTokenizer:
         n_chars = int(n_new / self.sampling_rate * self.framerate * C)
 
         if self._native:
-            window = torch.from_numpy(np.ascontiguousarray(self.tokenize_context)).to(self.device, non_blocking=True)
             frames_needed = -(-n_chars // C) if n_chars > 0 else 0          # 0 -> all frames
-            codes = self.codec_model.encode(window, keep_last_frames=frames_needed)  # [C,Fk] int64
-            per_channel = codes.cpu().numpy()[:, None, :]                   # [C,1,Fk]
+            sess = self._stream_session()
+            if self._session_audio_ok and 0 < n_new <= sess.cap_samples:
+                # steady state: only the new chunk crosses PCIe; the context lives in HBM
+                per_channel = sess.push_audio(new.reshape(C, -1), frames_needed)[:, None, :]
+            else:
+                window = torch.from_numpy(np.ascontiguousarray(self.tokenize_context)).to(self.device, non_blocking=True)
+                codes = self.codec_model.encode(window, keep_last_frames=frames_needed)  # [C,Fk] int64
+                per_channel = codes.cpu().numpy()[:, None, :]                   # [C,1,Fk]
+                # re-seed the device context with what the next call can still see
+                tail = self.tokenize_context[..., -self.context_samples:]
+                sess.reset()
+                self._session_audio_ok = tail.shape[-1] > 0
+                if self._session_audio_ok:
+                    sess.push_audio(tail, 1)
         else:
             window = torch.tensor(self.tokenize_context).to(self.device)
             with self._autocast():
@@ -147,9 +170,19 @@ class AudioTokenizer:
         want = int(self.get_audio_codes_str_secs(audio_codes_str) * self.sampling_rate) + preroll_samples
 
         if self._native:
-            dev_codes = torch.from_numpy(codes).to(self.device, non_blocking=True)
-            wav = self.codec_model.decode(dev_codes, keep_last_samples=want)  # [C,Tk] fp32
-            wav = wav[None]                                                   # [1,C,Tk]
+            n_new_frames = len(audio_codes_str) // C
+            sess = self._stream_session()
+            if self._session_codes_ok and 0 < n_new_frames <= sess.cap_frames:
+                new_codes = codes[:, codes.shape[1] - n_new_frames:]
+                wav = torch.from_numpy(sess.push_codes(new_codes, want))[None]      # [1,C,Tk]
+            else:
+                dev_codes = torch.from_numpy(codes).to(self.device, non_blocking=True)
+                wav = self.codec_model.decode(dev_codes, keep_last_samples=want)[None].cpu()   # [1,C,Tk] fp32
+                tail = codes[:, -(self.context_frames // C):]
+                sess.reset()
+                self._session_codes_ok = tail.shape[1] > 0
+                if self._session_codes_ok:
+                    sess.push_codes(tail, 1)
         else:
             dev_codes = torch.from_numpy(codes)[:, None, :].to(self.device)  # [C,1,F]
             with self._autocast():

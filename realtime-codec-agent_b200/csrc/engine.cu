@@ -667,3 +667,240 @@ int mc_op_attention(mc_handle* h, const void* qkv, void* out, int32_t B, int32_t
 }
 
 }  // extern "C"
+
+// =====================================================================================
+// Streaming sessions: the rolling 2.0 s context of AudioTokenizer.tokenize_audio /
+// detokenize_audio (audio_tokenizer.py:72-74,111-113) kept resident in HBM.  Each push uploads only
+// the new chunk, rebuilds the context in a ping-pong buffer, runs the batched encode/decode over the
+// channels and returns the kept frames/samples through pinned staging.  The whole sequence for a
+// given (context length, chunk length, keep) is captured once into a CUDA graph and replayed: the
+// steady state of the full-duplex loop is ONE graph launch per call.
+// =====================================================================================
+struct mc_stream {
+  mc_handle* h = nullptr;
+  int C = 1;
+  int ctx_samples = 32000, ctx_frames = 100;
+  int cap_samples = 0, cap_frames = 0;
+  float* audio[2] = {nullptr, nullptr};
+  int64_t* codes_ctx[2] = {nullptr, nullptr};
+  int audio_len = 0, code_len = 0, acur = 0, ccur = 0;
+  float* pin_audio = nullptr;   // [C, cap_samples]
+  int64_t* pin_codes = nullptr; // [C, cap_frames]
+  float* pin_wav = nullptr;     // [C, cap_samples]
+  int64_t* dev_codes_out = nullptr;
+  float* dev_wav_out = nullptr;
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int uses = 0; size_t arena_gen = 0; };
+  std::map<std::tuple<int, int, int, int, int>, GraphEntry> graphs;  // (kind, len_before, n, keep, parity)
+  bool use_graphs = true;
+  // work runs on the session's own stream (the caller's may be the legacy default stream, which cannot be
+  // captured); each push first orders it after everything already queued on the caller's stream
+  cudaStream_t own = nullptr;
+  cudaEvent_t order_ev = nullptr;
+  std::string err;
+};
+
+namespace {
+
+void stream_drop_graphs(mc_stream* s) {
+  for (auto& kv : s->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  s->graphs.clear();
+}
+
+// Runs `body` directly the first time a key is seen (that run sizes the workspace and fills the TMA
+// descriptor cache), captures it into a graph the second time, and replays the graph afterwards.
+template <typename Body>
+int run_or_replay(mc_stream* s, std::tuple<int, int, int, int, int> key, cudaStream_t stream, Body body) {
+  mc_handle* h = s->h;
+  if (!s->use_graphs || h->profiling) return body();
+  auto& e = s->graphs[key];
+  const size_t gen = reinterpret_cast<size_t>(h->arena) ^ h->arena_cap;
+  if (e.exec && e.arena_gen != gen) {
+    cudaGraphExecDestroy(e.exec);
+    e.exec = nullptr;
+    e.uses = 0;
+  }
+  if (e.exec) {
+    MC_CUDA(h, cudaGraphLaunch(e.exec, stream));
+    h->launches += 1;
+    return MC_OK;
+  }
+  if (e.uses++ == 0) return body();
+  MC_CUDA(h, cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
+  const int64_t launches_before = h->launches;
+  const int rc = body();
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+  h->launches = launches_before;
+  if (rc != MC_OK || ce != cudaSuccess || graph == nullptr) {
+    if (graph) cudaGraphDestroy(graph);
+    (void)cudaGetLastError();
+    s->use_graphs = false;  // fall back to direct launches for this session
+    return body();
+  }
+  ce = cudaGraphInstantiate(&e.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) {
+    e.exec = nullptr;
+    s->use_graphs = false;
+    return body();
+  }
+  e.arena_gen = reinterpret_cast<size_t>(h->arena) ^ h->arena_cap;
+  MC_CUDA(h, cudaGraphLaunch(e.exec, stream));
+  h->launches += 1;
+  return MC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mc_stream_create(mc_handle* h, int32_t channels, int32_t context_samples, int32_t max_chunk_samples, mc_stream** out) {
+  MC_ENTER(h);
+  if (!out || channels < 1 || context_samples < 1) return h->fail(MC_ERR_ARG, "mc_stream_create: bad arguments");
+  int hop = 1;
+  for (int i = 0; i < h->spec.n_convs; ++i) hop *= h->spec.conv_strides[i];
+  mc_stream* s = new mc_stream();
+  s->h = h; s->C = channels;
+  s->ctx_samples = context_samples;
+  s->ctx_frames = context_samples / hop;
+  s->cap_samples = std::max(context_samples, max_chunk_samples);
+  s->cap_frames = (s->cap_samples + hop - 1) / hop;
+  if (s->cap_frames > h->spec.max_positions) { delete s; return h->fail(MC_ERR_ARG, "mc_stream_create: context exceeds RoPE table"); }
+  const size_t ab = (size_t)channels * s->cap_samples * 4, cb = (size_t)channels * s->cap_frames * 8;
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaMalloc(&s->audio[i], ab);
+    if (e == cudaSuccess) e = cudaMalloc(&s->codes_ctx[i], cb);
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&s->dev_codes_out, cb);
+  if (e == cudaSuccess) e = cudaMalloc(&s->dev_wav_out, ab);
+  if (e == cudaSuccess) e = cudaMallocHost(&s->pin_audio, ab);
+  if (e == cudaSuccess) e = cudaMallocHost(&s->pin_codes, cb);
+  if (e == cudaSuccess) e = cudaMallocHost(&s->pin_wav, ab);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->order_ev, cudaEventDisableTiming);
+  if (e != cudaSuccess) { mc_stream_destroy(s); return h->fail(MC_ERR_NOMEM, "mc_stream_create: %s", cudaGetErrorString(e)); }
+  *out = s;
+  return MC_OK;
+}
+
+int mc_stream_destroy(mc_stream* s) {
+  if (!s) return MC_OK;
+  stream_drop_graphs(s);
+  for (int i = 0; i < 2; ++i) { if (s->audio[i]) cudaFree(s->audio[i]); if (s->codes_ctx[i]) cudaFree(s->codes_ctx[i]); }
+  if (s->dev_codes_out) cudaFree(s->dev_codes_out);
+  if (s->dev_wav_out) cudaFree(s->dev_wav_out);
+  if (s->pin_audio) cudaFreeHost(s->pin_audio);
+  if (s->pin_codes) cudaFreeHost(s->pin_codes);
+  if (s->pin_wav) cudaFreeHost(s->pin_wav);
+  if (s->order_ev) cudaEventDestroy(s->order_ev);
+  if (s->own) cudaStreamDestroy(s->own);
+  delete s;
+  return MC_OK;
+}
+
+int mc_stream_reset(mc_stream* s) {
+  if (!s) return MC_ERR_ARG;
+  s->audio_len = 0; s->code_len = 0;
+  return MC_OK;
+}
+
+/* chunk: HOST fp32 [C, n] (row stride n).  The context becomes the last max(n, context) samples of
+ * (context ++ chunk) — audio_tokenizer.py:72-74.  codes_out: HOST int64 [C, keep_frames] = the last
+ * keep_frames frames of the window (0 = all); *frames_out = frames written per channel.  Synchronises
+ * the stream before returning (the caller needs the codes). */
+int mc_stream_push_audio(mc_stream* s, const float* chunk, int32_t n, int32_t keep_frames, int64_t* codes_out,
+                         int32_t* frames_out, mc_stream_t stream_) {
+  if (!s) return MC_ERR_ARG;
+  mc_handle* h = s->h;
+  MC_ENTER(h);
+  cudaStream_t caller = (cudaStream_t)stream_;
+  MC_CUDA(h, cudaEventRecord(s->order_ev, caller));
+  MC_CUDA(h, cudaStreamWaitEvent(s->own, s->order_ev, 0));
+  cudaStream_t stream = s->own;
+  if (!chunk || !codes_out || n < 1) return h->fail(MC_ERR_ARG, "mc_stream_push_audio: bad arguments");
+  if (n > s->cap_samples) return h->fail(MC_ERR_ARG, "mc_stream_push_audio: chunk of %d samples exceeds the session capacity %d", n, s->cap_samples);
+  int hop = 1;
+  for (int i = 0; i < h->spec.n_convs; ++i) hop *= h->spec.conv_strides[i];
+  const int C = s->C, cap = s->cap_samples;
+  const int new_len = std::min(s->audio_len + n, std::max(n, s->ctx_samples));
+  const int keep_old = new_len - n;
+  const int F = (new_len + hop - 1) / hop;
+  const int keep = (keep_frames <= 0 || keep_frames > F) ? F : keep_frames;
+  for (int c = 0; c < C; ++c) memcpy(s->pin_audio + (size_t)c * cap, chunk + (size_t)c * n, (size_t)n * 4);
+  const int src = s->acur, dst = s->acur ^ 1;
+  const int old_len = s->audio_len;
+  auto body = [&]() -> int {
+    if (keep_old > 0)
+      MC_CUDA(h, cudaMemcpy2DAsync(s->audio[dst], (size_t)cap * 4, s->audio[src] + (old_len - keep_old), (size_t)cap * 4,
+                                   (size_t)keep_old * 4, C, cudaMemcpyDeviceToDevice, stream));
+    MC_CUDA(h, cudaMemcpy2DAsync(s->audio[dst] + keep_old, (size_t)cap * 4, s->pin_audio, (size_t)cap * 4, (size_t)n * 4, C,
+                                 cudaMemcpyHostToDevice, stream));
+    MC_TRY(encode_impl(h, s->audio[dst], cap, C, new_len, keep, s->dev_codes_out, nullptr, nullptr, stream));
+    MC_CUDA(h, cudaMemcpyAsync(s->pin_codes, s->dev_codes_out, (size_t)C * keep * 8, cudaMemcpyDeviceToHost, stream));
+    return MC_OK;
+  };
+  MC_TRY(run_or_replay(s, std::make_tuple(0, old_len, n, keep, src), stream, body));
+  MC_CUDA(h, cudaStreamSynchronize(stream));
+  memcpy(codes_out, s->pin_codes, (size_t)C * keep * 8);
+  if (frames_out) *frames_out = keep;
+  s->acur = dst;
+  s->audio_len = new_len;
+  return MC_OK;
+}
+
+/* codes: HOST int64 [C, n] appended to the code context (last max(n, context_frames) frames kept,
+ * audio_tokenizer.py:111-113); wav_out: HOST fp32 [C, keep_samples] = the last keep_samples samples of
+ * the decoded window (0 = all); *samples_out = samples written per channel. */
+int mc_stream_push_codes(mc_stream* s, const int64_t* codes, int32_t n, int32_t keep_samples, float* wav_out,
+                         int32_t* samples_out, mc_stream_t stream_) {
+  if (!s) return MC_ERR_ARG;
+  mc_handle* h = s->h;
+  MC_ENTER(h);
+  cudaStream_t caller = (cudaStream_t)stream_;
+  MC_CUDA(h, cudaEventRecord(s->order_ev, caller));
+  MC_CUDA(h, cudaStreamWaitEvent(s->own, s->order_ev, 0));
+  cudaStream_t stream = s->own;
+  if (!codes || !wav_out || n < 1) return h->fail(MC_ERR_ARG, "mc_stream_push_codes: bad arguments");
+  if (n > s->cap_frames) return h->fail(MC_ERR_ARG, "mc_stream_push_codes: %d frames exceed the session capacity %d", n, s->cap_frames);
+  int hop = 1;
+  for (int i = 0; i < h->spec.n_convs; ++i) hop *= h->spec.conv_strides[i];
+  const int C = s->C, cap = s->cap_frames;
+  const int new_len = std::min(s->code_len + n, std::max(n, s->ctx_frames));
+  const int keep_old = new_len - n;
+  const int total = new_len * hop;
+  const int keep = (keep_samples <= 0 || keep_samples > total) ? total : keep_samples;
+  for (int c = 0; c < C; ++c) memcpy(s->pin_codes + (size_t)c * cap, codes + (size_t)c * n, (size_t)n * 8);
+  const int src = s->ccur, dst = s->ccur ^ 1;
+  const int old_len = s->code_len;
+  // decode_impl wants dense [C, new_len] codes: the context buffers use row stride `cap`, so gather rows densely
+  auto body = [&]() -> int {
+    if (keep_old > 0)
+      MC_CUDA(h, cudaMemcpy2DAsync(s->codes_ctx[dst], (size_t)cap * 8, s->codes_ctx[src] + (old_len - keep_old), (size_t)cap * 8,
+                                   (size_t)keep_old * 8, C, cudaMemcpyDeviceToDevice, stream));
+    MC_CUDA(h, cudaMemcpy2DAsync(s->codes_ctx[dst] + keep_old, (size_t)cap * 8, s->pin_codes, (size_t)cap * 8, (size_t)n * 8, C,
+                                 cudaMemcpyHostToDevice, stream));
+    MC_CUDA(h, cudaMemcpy2DAsync(s->dev_codes_out, (size_t)new_len * 8, s->codes_ctx[dst], (size_t)cap * 8, (size_t)new_len * 8, C,
+                                 cudaMemcpyDeviceToDevice, stream));
+    MC_TRY(decode_impl(h, s->dev_codes_out, nullptr, C, new_len, keep, s->dev_wav_out, stream));
+    MC_CUDA(h, cudaMemcpyAsync(s->pin_wav, s->dev_wav_out, (size_t)C * keep * 4, cudaMemcpyDeviceToHost, stream));
+    return MC_OK;
+  };
+  MC_TRY(run_or_replay(s, std::make_tuple(1, old_len, n, keep, src), stream, body));
+  MC_CUDA(h, cudaStreamSynchronize(stream));
+  memcpy(wav_out, s->pin_wav, (size_t)C * keep * 4);
+  if (samples_out) *samples_out = keep;
+  s->ccur = dst;
+  s->code_len = new_len;
+  return MC_OK;
+}
+
+int mc_stream_set_graphs(mc_stream* s, int32_t enabled) {
+  if (!s) return MC_ERR_ARG;
+  s->use_graphs = enabled != 0;
+  if (!enabled) stream_drop_graphs(s);
+  return MC_OK;
+}
+
+}  // extern "C"

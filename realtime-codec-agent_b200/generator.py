@@ -117,6 +117,60 @@ def pack_weights(spec: MagiCodecSpec, w: Dict[str, torch.Tensor], max_positions:
     return {k: v.contiguous() for k, v in p.items()}
 
 
+# ------------------------------------------------------------------------------- streaming
+class StreamSession:
+    """Device-resident rolling context of one AudioTokenizer (mc_stream_* in the C ABI): each push
+    uploads only the new chunk / codes; the steady state replays one captured CUDA graph per call."""
+
+    def __init__(self, gen: "B200Generator", channels: int, context_samples: int, max_chunk_samples: int):
+        import numpy as np
+        self._np = np
+        self.gen, self.channels = gen, channels
+        self.cap_samples = max(context_samples, max_chunk_samples)
+        self.cap_frames = -(-self.cap_samples // gen.hop)
+        self._h = C.c_void_p()
+        rc = gen._lib.mc_stream_create(gen._handle, channels, context_samples, max_chunk_samples, C.byref(self._h))
+        nat.check(gen._lib, gen._handle, rc, "mc_stream_create")
+
+    def reset(self) -> None:
+        self.gen._lib.mc_stream_reset(self._h)
+
+    def set_graphs(self, enabled: bool) -> None:
+        self.gen._lib.mc_stream_set_graphs(self._h, 1 if enabled else 0)
+
+    def push_audio(self, chunk, keep_frames: int):
+        """chunk float32 [C,n] (numpy) -> int64 codes [C,keep] (numpy)."""
+        np = self._np
+        chunk = np.ascontiguousarray(chunk, dtype=np.float32).reshape(self.channels, -1)
+        n = chunk.shape[1]
+        out = np.empty((self.channels, self.cap_frames), dtype=np.int64)
+        got = C.c_int32(0)
+        rc = self.gen._lib.mc_stream_push_audio(self._h, chunk.ctypes.data, n, keep_frames, out.ctypes.data, C.byref(got),
+                                                self.gen._stream())
+        nat.check(self.gen._lib, self.gen._handle, rc, "mc_stream_push_audio")
+        return out.reshape(-1)[: self.channels * got.value].reshape(self.channels, got.value)
+
+    def push_codes(self, codes, keep_samples: int):
+        """codes int64 [C,n] (numpy) -> float32 wav [C,keep] (numpy)."""
+        np = self._np
+        codes = np.ascontiguousarray(codes, dtype=np.int64).reshape(self.channels, -1)
+        n = codes.shape[1]
+        out = np.empty((self.channels * self.cap_samples,), dtype=np.float32)
+        got = C.c_int32(0)
+        rc = self.gen._lib.mc_stream_push_codes(self._h, codes.ctypes.data, n, keep_samples, out.ctypes.data, C.byref(got),
+                                                self.gen._stream())
+        nat.check(self.gen._lib, self.gen._handle, rc, "mc_stream_push_codes")
+        return out[: self.channels * got.value].reshape(self.channels, got.value)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self.gen._handle:
+                self.gen._lib.mc_stream_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
 # --------------------------------------------------------------------------------- duck type
 class _Codebook:
     def __init__(self, raw: torch.Tensor):
@@ -220,6 +274,9 @@ class B200Generator:
     @property
     def launch_count(self) -> int:
         return int(self._lib.mc_launch_count(self._handle))
+
+    def open_stream(self, channels: int, context_samples: int, max_chunk_samples: int = 0) -> StreamSession:
+        return StreamSession(self, channels, context_samples, max(max_chunk_samples, context_samples))
 
     def set_debug_impl(self, attention: int = 0, vq: int = 0) -> None:
         nat.check(self._lib, self._handle, self._lib.mc_set_debug_impl(self._handle, attention, vq), "mc_set_debug_impl")

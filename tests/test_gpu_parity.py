@@ -200,3 +200,35 @@ def test_default_spec_shapes_and_determinism():
     assert len(tok.tokenize_audio(wav[:1600].cpu().numpy())) == 5
     emb = tok.get_codec_embeddings()
     assert emb.shape == (131072, 16) and torch.equal(emb, tok.get_codec_embeddings())
+
+
+def test_stream_session_equals_stateless_calls(bundle):
+    """mc_stream_* (device-resident context + CUDA-graph replay) == re-sending the whole window."""
+    name, spec, w, g, gen = bundle
+    wav = np.stack([g["wav0"], g["wav1"]])
+    sess = gen.open_stream(2, 32000)
+    ctx = np.zeros((2, 0), dtype=np.float32)
+    all_codes = []
+    pos = 0
+    for i, n in enumerate([320] * 4 + [1600] * 21 + [320] * 4 + [9280, 160, 1600]):
+        if pos + n > wav.shape[1]:
+            break
+        chunk = wav[:, pos:pos + n]
+        pos += n
+        ctx = np.concatenate([ctx, chunk], axis=1)[:, -max(n, 32000):]
+        keep = max(1, n // 320)
+        got = sess.push_audio(chunk, keep)
+        ref = gen.encode(torch.from_numpy(np.ascontiguousarray(ctx)).cuda(), keep_last_frames=keep).cpu().numpy()
+        assert np.array_equal(got, ref), f"push {i} (n={n})"
+        all_codes.append(got)
+    codes = np.concatenate(all_codes, axis=1)
+    cctx = np.zeros((2, 0), dtype=np.int64)
+    for i, n in enumerate([1] * 8 + [5] * 30 + [1] * 6):
+        if i * 3 + n > codes.shape[1]:
+            break
+        new = codes[:, i * 3: i * 3 + n]
+        cctx = np.concatenate([cctx, new], axis=1)[:, -max(n, 100):]
+        want = n * 320 + 320
+        got = sess.push_codes(new, want)
+        ref = gen.decode(torch.from_numpy(np.ascontiguousarray(cctx)).cuda(), keep_last_samples=want).cpu().numpy()
+        assert got.shape == ref.shape and np.array_equal(got, ref), f"push_codes {i}"
