@@ -33,7 +33,8 @@ struct GemmParams {
   int grp_in, grp_valid;          // rows per batch item in A / how many of them are real
   long long grp_stride, grp_off;  // output element offset = grp*grp_stride + grp_off + r*ldo
   int tma_store;  // 1: epilogue stages rows in smem and writes with TMA (store / reduce-add); 0: per-thread stores
-  const float* rope_cos;  // [rope_period, 32] or nullptr
+  const float* rope_cos;  // transposed table [32][rope_ld] or nullptr
+  int rope_ld;            // positions per table row (max_positions)
   const float* rope_sin;
   int rope_cols;    // RoPE applies to output columns [0, rope_cols), 64-wide heads
   int rope_period;  // position = rope_offset + (row within group) % rope_period
@@ -111,21 +112,18 @@ __device__ __forceinline__ void gemm_epilogue_slab(const GemmParams& p, const CU
           for (int j = 0; j < 64; ++j) v[j] = gelu_tanh_f(v[j]);
         }
         if (p.rope_cos != nullptr && n0 < p.rope_cols) {
-          // one 64-wide head per chunk: rotate (j, j+32) by the angle of (pos, j)
-          const float4* c4 = reinterpret_cast<const float4*>(p.rope_cos + static_cast<long long>(pos) * 32);
-          const float4* s4 = reinterpret_cast<const float4*>(p.rope_sin + static_cast<long long>(pos) * 32);
+          // one 64-wide head per chunk: rotate (j, j+32) by the angle of (pos, j).  The tables are stored
+          // TRANSPOSED ([32][rope_ld], position contiguous): lanes hold consecutive rows = consecutive
+          // positions, so each of these 64 scalar loads is one coalesced 128-byte request per warp.
+          const float* ct = p.rope_cos + pos;
+          const float* st = p.rope_sin + pos;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 cc = __ldg(c4 + (j >> 2));
-            const float4 ss = __ldg(s4 + (j >> 2));
-            const float cs[4] = {cc.x, cc.y, cc.z, cc.w};
-            const float sn[4] = {ss.x, ss.y, ss.z, ss.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float x1 = v[j + u], x2 = v[32 + j + u];
-              v[j + u] = x1 * cs[u] - x2 * sn[u];
-              v[32 + j + u] = x1 * sn[u] + x2 * cs[u];
-            }
+          for (int j = 0; j < 32; ++j) {
+            const float cs = __ldg(ct + static_cast<long long>(j) * p.rope_ld);
+            const float sn = __ldg(st + static_cast<long long>(j) * p.rope_ld);
+            const float x1 = v[j], x2 = v[32 + j];
+            v[j] = x1 * cs - x2 * sn;
+            v[32 + j] = x1 * sn + x2 * cs;
           }
         }
         if (p.tma_store) {

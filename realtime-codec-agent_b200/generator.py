@@ -56,7 +56,7 @@ def pack_weights(spec: MagiCodecSpec, w: Dict[str, torch.Tensor], max_positions:
       vq.codebook      fp32 [K,16]  = codebook_proj(codebook.weight), computed in fp32 on the CPU
       vq.c2            fp32 [K]     = |row|^2
       vq.packed        bf16 [K,64]  = [c_hi | c_lo | c_hi | n1 n2 n3 0...]  (vq_sm100.cuh)
-      rope.cos/.sin    fp32 [max_positions, 32]
+      rope.cos/.sin    fp32 [32, max_positions]   (transposed: coalesced per-row lookups in the QKV epilogue)
     """
     n = len(spec.conv_strides)
     BF16 = gemm_dtype          # tests pack in fp32 to check layouts exactly (tests/packed_emulator.py)
@@ -113,7 +113,7 @@ def pack_weights(spec: MagiCodecSpec, w: Dict[str, torch.Tensor], max_positions:
     packed[:, 48], packed[:, 49], packed[:, 50] = n1, n2, n3
     p["vq.packed"] = packed.contiguous()
     cos, sin = rope_tables(max_positions, spec.head_dim, spec.rope_base)
-    p["rope.cos"], p["rope.sin"] = cos, sin
+    p["rope.cos"], p["rope.sin"] = cos.t().contiguous(), sin.t().contiguous()   # [32, max_positions]: position contiguous
     return {k: v.contiguous() for k, v in p.items()}
 
 

@@ -28,7 +28,7 @@ def rmsnorm(x, g, eps):
 
 def layers(spec, p, prefix, n_layers, x, B, Fr):
     d, H = spec.d_model, spec.n_heads
-    cos, sin = p["rope.cos"][:Fr], p["rope.sin"][:Fr]
+    cos, sin = p["rope.cos"].t()[:Fr], p["rope.sin"].t()[:Fr]
     i = torch.arange(Fr)[:, None]
     j = torch.arange(Fr)[None, :]
     mask = (j >= i - spec.window_left) & (j <= i + spec.window_right)

@@ -94,7 +94,7 @@ def test_gemm_rope_epilogue(gen):
     W = (_rand((3 * d, 256), seed=12) / 16).to(torch.bfloat16)
     out = gen.op_gemm(A, W, out_mode=1, rope_cols=2 * d, rope_period=Fr)
     ref = (A.float() @ W.float().t()).view(B, Fr, 3, d // 64, 64)
-    cos, sin = gen._dev["rope.cos"][:Fr], gen._dev["rope.sin"][:Fr]
+    cos, sin = gen._dev["rope.cos"].t()[:Fr], gen._dev["rope.sin"].t()[:Fr]
 
     def rope(t):
         x1, x2 = t[..., :32], t[..., 32:]
