@@ -203,9 +203,10 @@ attention_window_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const _
 // v2: persistent, two-slot pipelined version of the same computation.  One CTA per SM walks the
 // (window, head, query-tile) items; while the four softmax warps work on item i in slot i&1, the
 // TMA warp is already loading item i+1 into the other slot and the MMA warp has issued its S=QK^T.
-//   warp 0  TMA producer      kv_full[s]   (tx)      <- slot_free[s]
-//   warp 1  MMA issuer        s_full[s], o_full[s]   <- kv_full[s], p_full[s]
-//   warps 2-5 / 6-9  softmax+output of slot 0 / slot 1:  p_full[s], slot_free[s] <- s_full[s], o_full[s]
+//   warps 0-3 / 4-7  softmax+output of slot 0 / slot 1:  p_full[s], slot_free[s] <- s_full[s], o_full[s]
+//   warp 8  TMA producer      kv_full[s]   (tx)      <- slot_free[s]
+//   warp 9  MMA issuer        s_full[s], o_full[s]   <- kv_full[s], p_full[s]
+//   (issuer warps carry the highest warp ids: the sub-partition arbiter prefers them)
 // The two softmax groups ping-pong: while one waits for its P*V to retire, the other is in its
 // softmax.  Each softmax thread needs only the 64 score columns its row can see (32q .. 32q+63),
 // read once from TMEM.  Masking is branch-free (masked scores become -inf, exp2 gives 0) and the row
@@ -251,7 +252,7 @@ attention_window_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, cons
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == 9) {
     tmem_alloc(tmem_ptr, ATT2_TMEM_COLS);
     tmem_relinquish();
   }
@@ -260,7 +261,7 @@ attention_window_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (warp == 8) {
     if (lane == 0) {
       int it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -278,7 +279,7 @@ attention_window_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, cons
         tma_load_2d(slot + ATT_SMEM_Q + ATT_SMEM_KV, &map_kv, &kv_full[s], 2 * d + h * 64, row_q - ATT_HALO);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, ATT_NKV, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, 64, 0, 1);
@@ -329,7 +330,7 @@ attention_window_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, cons
       }
     }
   } else {
-    const int group = (warp - 2) >> 2;         // softmax group = slot it serves
+    const int group = warp >> 2;               // softmax group = slot it serves (warps 0-3 / 4-7)
     const int q = warp & 3;                    // TMEM lane quarter
     const int r = q * 32 + lane;               // query row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
@@ -430,7 +431,7 @@ attention_window_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, cons
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, ATT2_TMEM_COLS);
   }

@@ -1,9 +1,12 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a:  D[M,N] = epilogue(A[M,K] * W[N,K]^T)
 //
-//   warp 0      TMA producer     (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
-//   warp 1      MMA issuer       (one thread: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16)
-//   warp 2      TMEM allocator   (2 x BN fp32 accumulator columns, double buffered)
-//   warps 4..7  epilogue         (tcgen05.ld -> bias / tanh-GELU / RoPE / residual -> global)
+//   warps 0..3  epilogue         (tcgen05.ld -> bias / tanh-GELU / RoPE / residual -> smem -> TMA store)
+//   warp 4      TMA producer     (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 5      MMA issuer       (one thread: tcgen05.mma.kind::f16, 128 x BN x 16 per CTA)
+//   warp 6      TMEM allocator   (2 x BN fp32 accumulator columns, double buffered)
+// The producer and the MMA issuer carry the HIGHEST warp ids on purpose: the SM sub-partition
+// arbiter prefers higher warp ids, and measured with clock64 an ALU-busy epilogue warp sharing a
+// sub-partition with a lower-numbered MMA thread delayed its tcgen05.mma issue by ~25 % per tile.
 //
 // The accumulator of tile i drains while the tensor pipe already works on tile i+1.
 //
@@ -70,147 +73,173 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Per-thread epilogue state that lives in registers across tiles.
+struct EpiRegs {
+  float bias[64];          // bias of the chunk about to be drained (prefetched one chunk ahead)
+  float rc[32], rs[32];    // cos / sin of this thread's row position (reloaded only when the row changes)
+  int rope_pos = -1;
+  int buf_sel = 0;
+};
+
+template <int BN>
+__device__ __forceinline__ void epi_load_bias(const GemmParams& p, int n0, float (&b)[64]) {
+#pragma unroll
+  for (int j = 0; j < 64; j += 4) {
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 + j < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+    b[j] = b4.x; b[j + 1] = b4.y; b[j + 2] = b4.z; b[j + 3] = b4.w;
+  }
+}
+
 // Drains one 128-row x BN accumulator slab: rows row_base + [0,128), columns n_base + [0,BN).
 // Called by the 4 epilogue warps (q = TMEM lane quarter); shared by the 1-CTA and 2-CTA kernels.
+// Everything that needs global memory (bias of the first chunk, RoPE angles of the row) is requested
+// BEFORE waiting for the accumulator, and each later chunk's bias is requested one chunk ahead, so no
+// L2 round trip sits between tcgen05.ld and the store (L1 is ~0 KB here: smem takes the whole 228 KB).
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue_slab(const GemmParams& p, const CUtensorMap* map_out_p, uint32_t tmem_acc,
                                                    int row_base, int n_base, int q, int lane, uint8_t* my_bufs,
-                                                   int& buf_sel) {
-      const int g = row_base + q * 32 + lane;  // A row handled by this thread
-      const int grp = g / p.grp_in;
-      const int r = g - grp * p.grp_in;
-      const bool row_ok = (g < p.M) && (r < p.grp_valid);
-      const long long obase = static_cast<long long>(grp) * p.grp_stride + p.grp_off + static_cast<long long>(r) * p.ldo;
-      const int pos = (p.rope_period > 0) ? (p.rope_offset + r % p.rope_period) : 0;
+                                                   EpiRegs& st, uint64_t* ready_bar, uint32_t ready_parity) {
+  const int g = row_base + q * 32 + lane;  // A row handled by this thread
+  const int grp = g / p.grp_in;
+  const int r = g - grp * p.grp_in;
+  const bool row_ok = (g < p.M) && (r < p.grp_valid);
+  const long long obase = static_cast<long long>(grp) * p.grp_stride + p.grp_off + static_cast<long long>(r) * p.ldo;
+  const bool has_bias = p.bias != nullptr;
+  if (has_bias) epi_load_bias<BN>(p, n_base, st.bias);
+  if (p.rope_period > 0) {
+    const int pos = p.rope_offset + r % p.rope_period;
+    if (pos != st.rope_pos) {
+      // transposed tables [32][rope_ld]: consecutive lanes = consecutive positions -> coalesced
+      st.rope_pos = pos;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        st.rc[j] = __ldg(p.rope_cos + static_cast<long long>(j) * p.rope_ld + pos);
+        st.rs[j] = __ldg(p.rope_sin + static_cast<long long>(j) * p.rope_ld + pos);
+      }
+    }
+  }
+  mbar_wait(ready_bar, ready_parity);  // accumulator complete
+  tc_fence_after();
 
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
-        const int n0 = n_base + c * 64;
-        if (n0 >= p.N) break;  // uniform across the warp
-        uint32_t raw0[32], raw1[32];
-        const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c * 64;
-        tmem_ld_32x32b_x32(taddr, raw0);
-        tmem_ld_32x32b_x32(taddr + 32, raw1);
-        tmem_ld_wait();
-        float v[64];
+  for (int c = 0; c < BN / 64; ++c) {
+    const int n0 = n_base + c * 64;
+    if (n0 >= p.N) break;  // uniform across the warp
+    uint32_t raw0[32], raw1[32];
+    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c * 64;
+    tmem_ld_32x32b_x32(taddr, raw0);
+    tmem_ld_32x32b_x32(taddr + 32, raw1);
+    tmem_ld_wait();
+    float v[64];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = __uint_as_float(raw0[j]);
-          v[32 + j] = __uint_as_float(raw1[j]);
-        }
-        if (p.bias != nullptr) {
+    for (int j = 0; j < 32; ++j) {
+      v[j] = __uint_as_float(raw0[j]);
+      v[32 + j] = __uint_as_float(raw1[j]);
+    }
+    if (has_bias) {
 #pragma unroll
-          for (int j = 0; j < 64; j += 4) {
-            if (n0 + j < p.N) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          }
-        }
-        if (p.act == ACT_GELU_TANH) {
+      for (int j = 0; j < 64; ++j) v[j] += st.bias[j];
+      if (c + 1 < BN / 64 && n0 + 64 < p.N) epi_load_bias<BN>(p, n0 + 64, st.bias);  // next chunk, in flight during this one
+    }
+    if (p.act == ACT_GELU_TANH) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = gelu_tanh_f(v[j]);
-        }
-        if (p.rope_cos != nullptr && n0 < p.rope_cols) {
-          // one 64-wide head per chunk: rotate (j, j+32) by the angle of (pos, j).  The tables are stored
-          // TRANSPOSED ([32][rope_ld], position contiguous): lanes hold consecutive rows = consecutive
-          // positions, so each of these 64 scalar loads is one coalesced 128-byte request per warp.
-          const float* ct = p.rope_cos + pos;
-          const float* st = p.rope_sin + pos;
+      for (int j = 0; j < 64; ++j) v[j] = gelu_tanh_f(v[j]);
+    }
+    if (p.rope_period > 0 && n0 < p.rope_cols) {
+      // one 64-wide head per chunk: rotate (j, j+32) by the angle of (row position, j)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float cs = __ldg(ct + static_cast<long long>(j) * p.rope_ld);
-            const float sn = __ldg(st + static_cast<long long>(j) * p.rope_ld);
-            const float x1 = v[j], x2 = v[32 + j];
-            v[j] = x1 * cs - x2 * sn;
-            v[32 + j] = x1 * sn + x2 * cs;
-          }
+      for (int j = 0; j < 32; ++j) {
+        const float x1 = v[j], x2 = v[32 + j];
+        v[j] = x1 * st.rc[j] - x2 * st.rs[j];
+        v[32 + j] = x1 * st.rs[j] + x2 * st.rc[j];
+      }
+    }
+    if (p.tma_store) {
+      // Stage this warp's 32 rows in smem (128-byte rows, 16-byte chunks XOR-swizzled by row so
+      // the row-per-thread writes are bank-conflict free), then one TMA store / reduce-add per
+      // box: global writes are full 128-byte lines and the fp32 residual is never read back.
+      const int row0 = row_base + q * 32;
+      const int sw = lane & 7;
+      if (p.out_mode == OUT_BF16) {
+        uint8_t* buf = my_bufs + st.buf_sel * kEpiBufBytes;
+        if (lane == 0) tma_wait_group_read<1>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 w;
+          w.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+          w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+          w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+          w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+          *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ sw) << 4)) = w;
         }
-        if (p.tma_store) {
-          // Stage this warp's 32 rows in smem (128-byte rows, 16-byte chunks XOR-swizzled by row so
-          // the row-per-thread writes are bank-conflict free), then one TMA store / reduce-add per
-          // box: global writes are full 128-byte lines and the fp32 residual is never read back.
-          const int row0 = row_base + q * 32;
-          const int sw = lane & 7;
-          if (p.out_mode == OUT_BF16) {
-            uint8_t* buf = my_bufs + buf_sel * kEpiBufBytes;
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(map_out_p, buf, n0, row0);
+          tma_commit_group();
+        }
+        st.buf_sel ^= 1;
+      } else {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (n0 + 32 * half < p.N) {  // uniform
+            uint8_t* buf = my_bufs + st.buf_sel * kEpiBufBytes;
             if (lane == 0) tma_wait_group_read<1>();
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              uint4 w;
-              w.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
-              w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-              w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-              w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ sw) << 4)) = w;
+              const float* vv = v + 32 * half + 4 * j;
+              *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ sw) << 4)) = make_float4(vv[0], vv[1], vv[2], vv[3]);
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(map_out_p, buf, n0, row0);
+              if (p.out_mode == OUT_F32_RESIDUAL) tma_reduce_add_2d(map_out_p, buf, n0 + 32 * half, row0);
+              else tma_store_2d(map_out_p, buf, n0 + 32 * half, row0);
               tma_commit_group();
             }
-            buf_sel ^= 1;
-          } else {
+            st.buf_sel ^= 1;
+          }
+        }
+      }
+    } else if (row_ok) {
+      if (p.out_mode == OUT_BF16) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + n0;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              if (n0 + 32 * half < p.N) {  // uniform
-                uint8_t* buf = my_bufs + buf_sel * kEpiBufBytes;
-                if (lane == 0) tma_wait_group_read<1>();
-                __syncwarp();
+        for (int j = 0; j < 64; j += 8) {
+          if (n0 + j < p.N) {
+            uint4 w;
+            w.x = pack_bf16x2(v[j], v[j + 1]);
+            w.y = pack_bf16x2(v[j + 2], v[j + 3]);
+            w.z = pack_bf16x2(v[j + 4], v[j + 5]);
+            w.w = pack_bf16x2(v[j + 6], v[j + 7]);
+            *reinterpret_cast<uint4*>(o + j) = w;
+          }
+        }
+      } else {
+        float* o = reinterpret_cast<float*>(p.out) + obase + n0;
+        if (p.out_mode == OUT_F32_RESIDUAL) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float* vv = v + 32 * half + 4 * j;
-                  *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ sw) << 4)) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                  if (p.out_mode == OUT_F32_RESIDUAL) tma_reduce_add_2d(map_out_p, buf, n0 + 32 * half, row0);
-                  else tma_store_2d(map_out_p, buf, n0 + 32 * half, row0);
-                  tma_commit_group();
-                }
-                buf_sel ^= 1;
-              }
+          for (int j = 0; j < 64; j += 4) {
+            if (n0 + j < p.N) {
+              float4 x = *reinterpret_cast<const float4*>(o + j);
+              x.x += v[j]; x.y += v[j + 1]; x.z += v[j + 2]; x.w += v[j + 3];
+              *reinterpret_cast<float4*>(o + j) = x;
             }
           }
-        } else if (row_ok) {
-          if (p.out_mode == OUT_BF16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + n0;
+        } else {
 #pragma unroll
-            for (int j = 0; j < 64; j += 8) {
-              if (n0 + j < p.N) {
-                uint4 w;
-                w.x = pack_bf16x2(v[j], v[j + 1]);
-                w.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                w.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                w.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(o + j) = w;
-              }
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(p.out) + obase + n0;
-            if (p.out_mode == OUT_F32_RESIDUAL) {
-#pragma unroll
-              for (int j = 0; j < 64; j += 4) {
-                if (n0 + j < p.N) {
-                  float4 x = *reinterpret_cast<const float4*>(o + j);
-                  x.x += v[j]; x.y += v[j + 1]; x.z += v[j + 2]; x.w += v[j + 3];
-                  *reinterpret_cast<float4*>(o + j) = x;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 64; j += 4) {
-                if (n0 + j < p.N) {
-                  *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                }
-              }
+          for (int j = 0; j < 64; j += 4) {
+            if (n0 + j < p.N) {
+              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
           }
         }
       }
+    }
+  }
 }
 
 template <int BN>
@@ -235,12 +264,12 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = p.K / GEMM_BK;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     if (p.tma_store) tma_prefetch_desc(&map_out);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == 5 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -251,7 +280,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     }
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 6) {
     tmem_alloc(tmem_ptr, Cfg::kTmemCols);
     tmem_relinquish();
   }
@@ -260,7 +289,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (warp == 4) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
@@ -281,7 +310,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 5) {
     // -------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
@@ -312,20 +341,18 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         umma_commit(&tmem_full[acc]);      // accumulator complete -> epilogue
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
     // ---------------------------------------------------------------- epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int q = warp;  // TMEM lane quarter this warp may read (warp id % 4)
     uint8_t* my_bufs = epi_base + q * 2 * kEpiBufBytes;
-    int buf_sel = 0;
+    EpiRegs st;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-
-      gemm_epilogue_slab<BN>(p, &map_out, tmem_base + acc * BN, m_blk * GEMM_BM, n_blk * BN, q, lane, my_bufs, buf_sel);
+      gemm_epilogue_slab<BN>(p, &map_out, tmem_base + acc * BN, m_blk * GEMM_BM, n_blk * BN, q, lane, my_bufs, st,
+                             &tmem_full[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -336,7 +363,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 6) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
@@ -390,12 +417,12 @@ gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = p.K / GEMM_BK;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     if (p.tma_store) tma_prefetch_desc(&map_out);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == 5 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 2);
       mbar_init(&empty_bar[s], 1);
@@ -406,7 +433,7 @@ gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     }
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 6) {
     tmem_alloc_pair(tmem_ptr, Cfg::kTmemCols);
     tmem_relinquish_pair();
   }
@@ -416,7 +443,7 @@ gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (warp == 4) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -438,7 +465,7 @@ gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 5) {
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN, 0, 0);
       int stage = 0;
@@ -465,19 +492,17 @@ gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         umma_commit_pair(&tmem_full[acc], 3);
       }
     }
-  } else if (warp >= 4) {
-    const int q = warp & 3;
+  } else if (warp < 4) {
+    const int q = warp;
     uint8_t* my_bufs = epi_base + q * 2 * kEpiBufBytes;
-    int buf_sel = 0;
+    EpiRegs st;
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       gemm_epilogue_slab<BN>(p, &map_out, tmem_base + acc * BN, m_blk * 2 * GEMM_BM + rank * GEMM_BM, n_blk * BN, q, lane,
-                             my_bufs, buf_sel);
+                             my_bufs, st, &tmem_full[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
@@ -489,7 +514,7 @@ gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // the peer's smem / barriers stay alive until the leader's last MMA and commit retired
-  if (warp == 2) {
+  if (warp == 6) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
   }

@@ -78,6 +78,69 @@ def diag_gemm():
     print(f"cublas same shape: {ms:.3f} ms  {2 * 25600 * 4096 * 1024 / ms / 1e9:.1f} TFLOP/s")
 
 
+def diag_epi():
+    """Isolated timing of the K=1024 GEMM shapes of one transformer block under each epilogue mode."""
+    gen = make_gen(pkg.DEFAULT_SPEC)
+    torch.manual_seed(0)
+    M = 25600
+
+    def timeit(fn, flops, label):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        print(f"{label:58s} {ms*1e3:8.1f} us  {flops / ms / 1e9:7.1f} TFLOP/s")
+
+    for (N, K) in [(3072, 1024), (1024, 1024), (4096, 1024), (1024, 4096)]:
+        A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+        W = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
+        bias = torch.randn(N, device="cuda")
+        ob = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        of = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+        fl = 2.0 * M * N * K
+        timeit(lambda: gen.op_gemm(A, W, out_mode=0, out=ob), fl, f"N{N} K{K} bf16 out")
+        timeit(lambda: gen.op_gemm(A, W, act=0x100, out_mode=0, out=ob), fl, f"N{N} K{K} EXPERIMENT tmem drain only, no stores")
+        timeit(lambda: gen.op_gemm(A, W, act=0x200, out_mode=0, out=ob), fl, f"N{N} K{K} EXPERIMENT mainloop only")
+        timeit(lambda: gen.op_gemm(A, W, bias=bias, act=0x101, out_mode=0, out=ob), fl, f"N{N} K{K} EXPERIMENT drain + bias + gelu, no stores")
+        timeit(lambda: gen.op_gemm(A, W, bias=bias, out_mode=0, out=ob), fl, f"N{N} K{K} bf16 out + bias")
+        timeit(lambda: gen.op_gemm(A, W, bias=bias, act=1, out_mode=0, out=ob), fl, f"N{N} K{K} bf16 out + bias + gelu")
+        if N == 3072:
+            timeit(lambda: gen.op_gemm(A, W, bias=bias, out_mode=0, out=ob, rope_cols=2048, rope_period=100), fl,
+                   f"N{N} K{K} bf16 out + bias + rope")
+        timeit(lambda: gen.op_gemm(A, W, bias=bias, out_mode=1, out=of), fl, f"N{N} K{K} f32 out + bias")
+        timeit(lambda: gen.op_gemm(A, W, bias=bias, out_mode=2, out=of), fl, f"N{N} K{K} f32 residual + bias")
+        timeit(lambda: gen.op_gemm(A, W, bias=bias, out_mode=0, out=ob, block_n=256), fl, f"N{N} K{K} bf16 out + bias, single-CTA bn256")
+        ref = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        timeit(lambda: torch.matmul(A, W.t(), out=ref), fl, f"N{N} K{K} cuBLAS")
+
+
+def diag_epi_cycles():
+    gen = make_gen(pkg.DEFAULT_SPEC)
+    M, N, K = 25600, 4096, 1024
+    A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(N, K, device="cuda") / 32).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    ob = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    of = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    for label, kw in [("mainloop only", dict(act=0x600)), ("drain only", dict(act=0x500)), ("bf16 store", dict(act=0x400)),
+                      ("bias+gelu no store", dict(act=0x501, bias=bias)), ("bias+gelu bf16 store", dict(act=0x401, bias=bias)),
+                      ("bias bf16 store", dict(act=0x400, bias=bias))]:
+        for _ in range(2):
+            gen.op_gemm(A, W, out_mode=0, out=ob, **{k: v for k, v in kw.items() if k != "act"}, act=kw["act"] & ~0x400)
+        torch.cuda.synchronize()
+        print("----", label, flush=True)
+        gen.op_gemm(A, W, out_mode=0, out=ob, **kw)
+        torch.cuda.synchronize()
+    print("---- f32 residual + bias", flush=True)
+    gen.op_gemm(A, W, bias=bias, out_mode=2, out=of, act=0x400)
+    torch.cuda.synchronize()
+
+
 def diag_attn():
     gen = make_gen()
     spec = gen.spec
@@ -119,4 +182,4 @@ def diag_e2e():
 
 
 if __name__ == "__main__":
-    {"gemm": diag_gemm, "attn": diag_attn, "vq": diag_vq, "e2e": diag_e2e}[sys.argv[1]]()
+    {"gemm": diag_gemm, "attn": diag_attn, "vq": diag_vq, "e2e": diag_e2e, "epi": diag_epi, "cyc": diag_epi_cycles}[sys.argv[1]]()
