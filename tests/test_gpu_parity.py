@@ -21,11 +21,14 @@ from oracle.magicodec_oracle import OracleGenerator
 
 pytestmark = pytest.mark.gpu
 
-Z_TOL = 0.08
-EPS_MARGIN = 0.35
-NEAR_TIE_MAX = 0.45
-SNR_MIN_DB = 30.0
-WAV_TOL = 0.05
+# Calibrated on profiles/r01_parity_sweep.jsonl (4000 + 4000 + 2400 frames over three specs): measured
+# max|dz| 0.031-0.035 (rms 0.0066 = 0.7 % of the latent rms), every disagreeing frame has an oracle
+# margin <= 0.101, 97.8-98.7 % of ALL frames agree, decode SNR 42.6-44.2 dB, max-abs 0.7-0.9 % of peak.
+Z_TOL = 0.06
+EPS_MARGIN = 0.15
+NEAR_TIE_MAX = 0.30
+SNR_MIN_DB = 38.0
+WAV_TOL = 0.02
 
 SPECS = {"tiny": pkg.TINY_SPEC, "mid": pkg.MID_SPEC}
 
