@@ -44,7 +44,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch-size", type=int, default=256)
+    ap.add_argument("--batch-size", type=int, default=256, help="windows per batch (the reference CLI's --batch_size)")
+    ap.add_argument("--fuse-batches", type=int, default=4, help="consecutive batches issued as one engine launch "
+                    "(results are independent of launch grouping; tests/test_gpu_parity.py checks this bit-exactly)")
     ap.add_argument("--file-secs", type=float, default=FILE_SECS)
     ap.add_argument("--files", type=int, default=FILES_PER_RANK)
     ap.add_argument("--cpu-sample-secs", type=float, default=0.0, help="0 = pick ~15 s of CPU work")
@@ -137,8 +139,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
     config = {"workload": f"1 h synthetic 16 kHz mono per GPU ({args.files} x {args.file_secs:.0f} s files), chunk 0.1 s, "
-                          f"context 2.0 s, batch {args.batch_size} windows, MagiCodec default spec (8+8 layers, d=1024), "
-                          "random-init weights seed 0",
+                          f"context 2.0 s, batch {args.batch_size} windows ({args.fuse_batches} batches fused per engine "
+                          f"launch), MagiCodec default spec (8+8 layers, d=1024), random-init weights seed 0",
               "windows_per_step_per_gpu": int(args.files * args.file_secs * 10), "l2": "inputs_exceed_l2",
               "sharding": "files across ranks, no data-path collective; manifest all_gather per step at N>1"}
 
@@ -177,7 +179,7 @@ def main():
         return corpus.gather_manifests(local, dev)
 
     def step_device():
-        codes = corpus.encode_streams(gen, dev_files, 0.1, 2.0, args.batch_size)
+        codes = corpus.encode_streams(gen, dev_files, 0.1, 2.0, args.batch_size, args.fuse_batches)
         if world > 1:
             manifests(codes)
         return codes
@@ -187,7 +189,7 @@ def main():
     def step_e2e():
         for s, h in zip(staging, host_files):
             s.copy_(h, non_blocking=True)
-        codes = corpus.encode_streams(gen, staging, 0.1, 2.0, args.batch_size)
+        codes = corpus.encode_streams(gen, staging, 0.1, 2.0, args.batch_size, args.fuse_batches)
         for hc, c in zip(host_codes, codes):
             hc.copy_(c, non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -64,8 +64,13 @@ def plan_stream(n_samples: int, chunk_samples: int, context_samples: int, sample
 
 
 def encode_streams(gen, streams: Sequence[torch.Tensor], chunk_secs: float = 0.1, context_secs: float = 2.0,
-                   batch_size: int = 256) -> List[torch.Tensor]:
-    """Encode mono streams (1-D fp32 device tensors) -> one int64 code tensor per stream."""
+                   batch_size: int = 256, fuse_batches: int = 1) -> List[torch.Tensor]:
+    """Encode mono streams (1-D fp32 device tensors) -> one int64 code tensor per stream.
+
+    ``batch_size`` is the reference CLI's windows-per-forward flag.  Per-window results do not depend on
+    how windows are grouped into launches (tested bit-exact), so ``fuse_batches`` consecutive batches may
+    be issued as ONE engine call: fewer, larger launches quantise better onto 74 CTA pairs."""
+    batch_size = batch_size * max(1, int(fuse_batches))
     sr, hop = gen.sample_rate, gen.hop
     framerate = sr / hop
     chunk = int(chunk_secs * sr)
