@@ -14,6 +14,11 @@
  *   mc_vq_search                              model.quantizer.inference    audio_tokenizer.py:192
  *   mc_codebook                               quantizer.codebook_proj(quantizer.codebook.weight)
  *                                                                          audio_tokenizer.py:158,198
+ *   mc_stream_set_emit / _push_codes_emit     RealtimeAgent.detokenize_output_chunk: detokenize_audio ->
+ *                                             pad_or_trim -> normalize_audio_rms -> smooth_join
+ *                                             realtime_agent_v2.py:556-579, utils/audio_utils.py:4-46
+ *   mc_embed_distance                         F.embedding + vector_norm + mean of
+ *                                             ExternalTTSDuplexAligner  external_tts_duplex_aligner.py:14-27
  *   mc_op_*                                   the library kernels underneath (cuDNN conv1d, cuBLAS /
  *                                             fused_dense_lib linears, flash-attn local attention,
  *                                             csrc/layer_norm, csrc/rotary; magicodec_build.sh:4-16)
@@ -105,7 +110,8 @@ int mc_codebook(mc_handle* h, float* out, mc_stream_t stream);
 typedef struct mc_stream mc_stream;
 int mc_stream_create(mc_handle* h, int32_t channels, int32_t context_samples, int32_t max_chunk_samples, mc_stream** out);
 int mc_stream_destroy(mc_stream* s);
-int mc_stream_reset(mc_stream* s);                      /* AudioTokenizer.reset_context, :44-46 */
+int mc_stream_reset(mc_stream* s);                      /* AudioTokenizer.reset_context, :44-46 (also forgets the emit chain's previous chunk) */
+int mc_stream_reset_part(mc_stream* s, int32_t audio, int32_t codes); /* drop only the audio and/or the code context */
 /* chunk fp32 [C,n]; codes_out int64 [C,keep_frames] (0 = every frame of the window). */
 int mc_stream_push_audio(mc_stream* s, const float* chunk, int32_t n, int32_t keep_frames, int64_t* codes_out,
                          int32_t* frames_out, mc_stream_t stream);
@@ -113,6 +119,25 @@ int mc_stream_push_audio(mc_stream* s, const float* chunk, int32_t n, int32_t ke
 int mc_stream_push_codes(mc_stream* s, const int64_t* codes, int32_t n, int32_t keep_samples, float* wav_out,
                          int32_t* samples_out, mc_stream_t stream);
 int mc_stream_set_graphs(mc_stream* s, int32_t enabled); /* 0: direct launches (A/B timing, debugging) */
+
+/* ---- post-decode emit chain of the agent loop (mono sessions), fused behind the decoder in the same
+ * CUDA graph: detokenize_audio(codes, preroll = fade) -> pad_or_trim -> normalize_audio_rms (skipped when
+ * target_rms <= 0) -> smooth_join with the previous chunk -> the chunk to emit.
+ * set_emit: chunk_samples = agent chunk (n codes * hop), fade_samples = L of create_crossfade_ramps,
+ * fade_in = HOST fp32 [L] rising ramp (fade_out is its mirror).  Resets the "previous chunk" state.
+ * push_codes_emit: codes HOST int64 [n]; out HOST fp32 [2*chunk + L] = emitted chunk [chunk] ++ the L
+ * cross-faded samples that replace the tail of the previous history chunk ++ the new history chunk
+ * [chunk]; *had_prev = whether a previous chunk existed (0 on the first call after create/reset/set_emit). */
+int mc_stream_set_emit(mc_stream* s, int32_t chunk_samples, int32_t fade_samples, float target_rms,
+                       float silence_rms_threshold, const float* fade_in);
+int mc_stream_push_codes_emit(mc_stream* s, const int64_t* codes, int32_t n, float* out, int32_t* had_prev,
+                              mc_stream_t stream);
+
+/* ids DEVICE int64 [rows, n] (LM token ids; code = id - vocab_start, clamped to the codebook).
+ * dist_out DEVICE fp32 [rows] (optional) = mean_j ||E[code_j] - ref||_2, ref DEVICE fp32 [dq] (NULL = 0);
+ * mean_out DEVICE fp32 [rows, dq] (optional) = mean_j E[code_j], E = the cached projected codebook. */
+int mc_embed_distance(mc_handle* h, const int64_t* ids, int32_t rows, int32_t n, int64_t vocab_start, const float* ref,
+                      float* dist_out, float* mean_out, mc_stream_t stream);
 
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t mc_launch_count(const mc_handle* h);
@@ -142,6 +167,15 @@ int mc_op_rmsnorm(mc_handle* h, const float* x, const float* gamma, void* out_bf
 /* qkv bf16 [B*F, 3*d] (RoPE applied) -> out bf16 [B*F, d]. */
 int mc_op_attention(mc_handle* h, const void* qkv, void* out, int32_t B, int32_t F, int32_t impl,
                     mc_stream_t stream);
+
+/* The two kernels behind mc_stream_push_codes_emit / mc_embed_distance on caller-supplied DEVICE buffers
+ * (the golden-vector replays of tests/test_gpu_post.py): wav [n_have], fade_in / prev_tail [fade] (prev_tail is
+ * updated in place), out [2*chunk + fade]; table fp32 [K,16]. */
+int mc_op_emit_chunk(mc_handle* h, const float* wav, int32_t n_have, int32_t chunk, int32_t fade, int32_t has_prev,
+                     float target_rms, float silence_rms_threshold, const float* fade_in, float* prev_tail, float* out,
+                     mc_stream_t stream);
+int mc_op_embed_distance(mc_handle* h, const float* table, int32_t K, const int64_t* ids, int32_t rows, int32_t n,
+                         int64_t vocab_start, const float* ref, float* dist_out, float* mean_out, mc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -9,12 +9,18 @@ Public surface (mirrors the reference's interface for this path):
     codes_to_chars / chars_to_codes / UNICODE_OFFSET(_LARGE)   — codec_bpe converter
     B200Generator             — the model duck type of audio_tokenizer.py:28-36,158,190-200
     MagiCodecSpec, DEFAULT_SPEC, init_random_weights
+    smooth_join / create_crossfade_ramps / pad_or_trim / normalize_audio_rms   — utils/audio_utils.py:4-46
+    OutputChunkEmitter        — RealtimeAgent.detokenize_output_chunk, realtime_agent_v2.py:556-579
+    ExternalTTSDuplexAligner  — external_tts_duplex_aligner.py:6-27
 """
 from .spec import MagiCodecSpec, DEFAULT_SPEC, TINY_SPEC, MID_SPEC  # noqa: F401
 from .weights import init_random_weights, param_shapes, save_checkpoint, load_checkpoint  # noqa: F401
 from .codec_chars import codes_to_chars, chars_to_codes, UNICODE_OFFSET, UNICODE_OFFSET_LARGE  # noqa: F401
 from .audio_tokenizer import AudioTokenizer, load_magicodec_model  # noqa: F401
 from .synth import synth_audio  # noqa: F401
+from .audio_utils import smooth_join, create_crossfade_ramps, pad_or_trim, normalize_audio_rms  # noqa: F401
+from .output_chunks import OutputChunkEmitter  # noqa: F401
+from .duplex_aligner import ExternalTTSDuplexAligner  # noqa: F401
 
 
 def __getattr__(name):

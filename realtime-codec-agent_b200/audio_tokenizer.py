@@ -133,7 +133,7 @@ class AudioTokenizer:
                 per_channel = codes.cpu().numpy()[:, None, :]                   # [C,1,Fk]
                 # re-seed the device context with what the next call can still see
                 tail = self.tokenize_context[..., -self.context_samples:]
-                sess.reset()
+                sess.reset_audio()
                 self._session_audio_ok = tail.shape[-1] > 0
                 if self._session_audio_ok:
                     sess.push_audio(tail, 1)
@@ -179,7 +179,7 @@ class AudioTokenizer:
                 dev_codes = torch.from_numpy(codes).to(self.device, non_blocking=True)
                 wav = self.codec_model.decode(dev_codes, keep_last_samples=want)[None].cpu()   # [1,C,Tk] fp32
                 tail = codes[:, -(self.context_frames // C):]
-                sess.reset()
+                sess.reset_codes()
                 self._session_codes_ok = tail.shape[1] > 0
                 if self._session_codes_ok:
                     sess.push_codes(tail, 1)
@@ -192,6 +192,35 @@ class AudioTokenizer:
         preroll_left = max(0, preroll_samples - want + wav.shape[-1])
         out = wav[0, 0] if C == 1 else wav[0]
         return (self.sampling_rate, out.cpu().numpy()), end_hanging, preroll_left
+
+    # ------------------------------------------------- decode + emit chain (native engine only)
+    def arm_emit(self, chunk_samples: int, fade_samples: int, target_rms: float, silence_rms_threshold: float,
+                 fade_in: np.ndarray) -> None:
+        """Configure the device-side output chain (OutputChunkEmitter); forgets the previous chunk."""
+        if not self._native:
+            raise RuntimeError("the fused emit chain needs the B200 engine")
+        self._stream_session().set_emit(chunk_samples, fade_samples, target_rms, silence_rms_threshold, fade_in)
+
+    @torch.inference_mode()
+    def detokenize_audio_emit(self, audio_codes_str: str):
+        """detokenize_audio(str, preroll_samples=L) + pad_or_trim + normalize_audio_rms + smooth_join in one
+        engine call.  Context bookkeeping is that of detokenize_audio (:105-113).  Returns
+        (float32[2*chunk + L] = emitted ++ cross-faded tail of the previous chunk ++ new history chunk, had_prev)."""
+        audio_codes_str, _ = self._drop_hanging_channel_codes(audio_codes_str)
+        before = self.detokenize_context
+        self.detokenize_context += audio_codes_str
+        keep = max(len(audio_codes_str), self.context_frames)
+        self.detokenize_context = self.detokenize_context[-keep:]
+        sess = self._stream_session()
+        if not self._session_codes_ok:
+            # device context out of step with the string (a one-shot decode ran in between): re-seed it
+            sess.reset_codes()
+            tail = before[-self.context_frames:]
+            if tail:
+                sess.push_codes(chars_to_codes(tail, 1, self.codebook_size, unicode_offset=self.unicode_offset), 1)
+            self._session_codes_ok = True
+        new_codes = chars_to_codes(audio_codes_str, 1, self.codebook_size, unicode_offset=self.unicode_offset)
+        return sess.push_codes_emit(new_codes)
 
     # ---------------------------------------------------------- codec details
     @torch.inference_mode()

@@ -6,6 +6,7 @@
 #include "attn_vq_simt.cuh"
 #include "elementwise.cuh"
 #include "gemm_sm100.cuh"
+#include "post_sm100.cuh"
 #include "vq_sm100.cuh"
 
 using namespace mc;
@@ -606,6 +607,40 @@ int mc_codebook(mc_handle* h, float* out, mc_stream_t stream) {
   return MC_OK;
 }
 
+int mc_embed_distance(mc_handle* h, const int64_t* ids, int32_t rows, int32_t n, int64_t vocab_start, const float* ref,
+                      float* dist_out, float* mean_out, mc_stream_t stream) {
+  MC_ENTER(h);
+  if (!ids || rows < 1 || n < 1 || (!dist_out && !mean_out)) return h->fail(MC_ERR_ARG, "mc_embed_distance: bad arguments");
+  embed_distance_kernel<<<rows, POST_THREADS, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const long long*>(ids), n, (long long)vocab_start, h->ptr<float>("vq.codebook"), h->spec.codebook_size,
+      ref, dist_out, mean_out);
+  MC_LAUNCH_CHECK(h, "embed_distance_kernel");
+  return MC_OK;
+}
+
+int mc_op_embed_distance(mc_handle* h, const float* table, int32_t K, const int64_t* ids, int32_t rows, int32_t n,
+                         int64_t vocab_start, const float* ref, float* dist_out, float* mean_out, mc_stream_t stream) {
+  MC_ENTER(h);
+  if (!table || K < 1 || !ids || rows < 1 || n < 1 || (!dist_out && !mean_out))
+    return h->fail(MC_ERR_ARG, "mc_op_embed_distance: bad arguments");
+  embed_distance_kernel<<<rows, POST_THREADS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(ids), n,
+                                                                         (long long)vocab_start, table, K, ref, dist_out, mean_out);
+  MC_LAUNCH_CHECK(h, "embed_distance_kernel");
+  return MC_OK;
+}
+
+int mc_op_emit_chunk(mc_handle* h, const float* wav, int32_t n_have, int32_t chunk, int32_t fade, int32_t has_prev,
+                     float target_rms, float silence_rms_threshold, const float* fade_in, float* prev_tail, float* out,
+                     mc_stream_t stream) {
+  MC_ENTER(h);
+  if (!wav || !fade_in || !prev_tail || !out || chunk < 1 || fade < 1 || fade > chunk || n_have < 1)
+    return h->fail(MC_ERR_ARG, "mc_op_emit_chunk: bad arguments");
+  emit_chunk_kernel<<<1, POST_THREADS, 0, (cudaStream_t)stream>>>(wav, n_have, chunk, fade, has_prev, target_rms,
+                                                                  silence_rms_threshold, fade_in, prev_tail, out);
+  MC_LAUNCH_CHECK(h, "emit_chunk_kernel");
+  return MC_OK;
+}
+
 int64_t mc_launch_count(const mc_handle* h) { return h ? h->launches : 0; }
 
 int mc_profile_begin(mc_handle* h) {
@@ -699,6 +734,13 @@ struct mc_stream {
   cudaStream_t own = nullptr;
   cudaEvent_t order_ev = nullptr;
   std::string err;
+  // post-decode emit chain (mc_stream_set_emit / mc_stream_push_codes_emit)
+  int emit_chunk = 0, emit_fade = 0, emit_has_prev = 0;
+  float emit_target_rms = 0.f, emit_silence_thr = 0.f;
+  float* emit_fade_in = nullptr;   // device [fade]
+  float* emit_prev_tail = nullptr; // device [fade]
+  float* emit_out = nullptr;       // device [2*chunk + fade]
+  float* pin_emit = nullptr;       // pinned  [2*chunk + fade]
 };
 
 namespace {
@@ -796,6 +838,10 @@ int mc_stream_destroy(mc_stream* s) {
   if (s->pin_audio) cudaFreeHost(s->pin_audio);
   if (s->pin_codes) cudaFreeHost(s->pin_codes);
   if (s->pin_wav) cudaFreeHost(s->pin_wav);
+  if (s->emit_fade_in) cudaFree(s->emit_fade_in);
+  if (s->emit_prev_tail) cudaFree(s->emit_prev_tail);
+  if (s->emit_out) cudaFree(s->emit_out);
+  if (s->pin_emit) cudaFreeHost(s->pin_emit);
   if (s->order_ev) cudaEventDestroy(s->order_ev);
   if (s->own) cudaStreamDestroy(s->own);
   delete s;
@@ -805,6 +851,14 @@ int mc_stream_destroy(mc_stream* s) {
 int mc_stream_reset(mc_stream* s) {
   if (!s) return MC_ERR_ARG;
   s->audio_len = 0; s->code_len = 0;
+  s->emit_has_prev = 0;
+  return MC_OK;
+}
+
+int mc_stream_reset_part(mc_stream* s, int32_t audio, int32_t codes) {
+  if (!s) return MC_ERR_ARG;
+  if (audio) s->audio_len = 0;
+  if (codes) s->code_len = 0;
   return MC_OK;
 }
 
@@ -854,9 +908,11 @@ int mc_stream_push_audio(mc_stream* s, const float* chunk, int32_t n, int32_t ke
 
 /* codes: HOST int64 [C, n] appended to the code context (last max(n, context_frames) frames kept,
  * audio_tokenizer.py:111-113); wav_out: HOST fp32 [C, keep_samples] = the last keep_samples samples of
- * the decoded window (0 = all); *samples_out = samples written per channel. */
-int mc_stream_push_codes(mc_stream* s, const int64_t* codes, int32_t n, int32_t keep_samples, float* wav_out,
-                         int32_t* samples_out, mc_stream_t stream_) {
+ * the decoded window (0 = all); *samples_out = samples written per channel.
+ * emit = true (mc_stream_push_codes_emit): keep = chunk + fade samples, followed IN THE SAME GRAPH by
+ * emit_chunk_kernel; wav_out then receives the kernel's [2*chunk + fade] output block. */
+static int stream_push_codes_impl(mc_stream* s, const int64_t* codes, int32_t n, int32_t keep_samples, bool emit,
+                                  float* wav_out, int32_t* samples_out, mc_stream_t stream_) {
   if (!s) return MC_ERR_ARG;
   mc_handle* h = s->h;
   MC_ENTER(h);
@@ -872,10 +928,24 @@ int mc_stream_push_codes(mc_stream* s, const int64_t* codes, int32_t n, int32_t 
   const int new_len = std::min(s->code_len + n, std::max(n, s->ctx_frames));
   const int keep_old = new_len - n;
   const int total = new_len * hop;
-  const int keep = (keep_samples <= 0 || keep_samples > total) ? total : keep_samples;
+  int keep = (keep_samples <= 0 || keep_samples > total) ? total : keep_samples;
+  const int has_prev = s->emit_has_prev;
+  if (emit) {
+    if (C != 1) return h->fail(MC_ERR_ARG, "mc_stream_push_codes_emit: the emit chain is mono (pad_or_trim rejects [C,T])");
+    if (s->emit_chunk <= 0) return h->fail(MC_ERR_STATE, "mc_stream_push_codes_emit: call mc_stream_set_emit first");
+    if (n * hop != s->emit_chunk)
+      return h->fail(MC_ERR_ARG, "mc_stream_push_codes_emit: %d codes decode to %d samples, chunk is %d", n, n * hop, s->emit_chunk);
+    keep = std::min(total, s->emit_chunk + s->emit_fade);
+    // realtime_agent_v2.py:566-568 asserts the joined length; the same conditions fail here, before any work
+    if (has_prev && keep != s->emit_chunk + s->emit_fade)
+      return h->fail(MC_ERR_STATE, "mc_stream_push_codes_emit: only %d decoded samples for chunk %d + fade %d", keep, s->emit_chunk, s->emit_fade);
+    if (!has_prev && keep != s->emit_chunk)
+      return h->fail(MC_ERR_STATE, "mc_stream_push_codes_emit: the first emitted chunk needs an empty code context (reset first)");
+  }
   for (int c = 0; c < C; ++c) memcpy(s->pin_codes + (size_t)c * cap, codes + (size_t)c * n, (size_t)n * 8);
   const int src = s->ccur, dst = s->ccur ^ 1;
   const int old_len = s->code_len;
+  const int emit_floats = 2 * s->emit_chunk + s->emit_fade;
   // decode_impl wants dense [C, new_len] codes: the context buffers use row stride `cap`, so gather rows densely
   auto body = [&]() -> int {
     if (keep_old > 0)
@@ -886,16 +956,69 @@ int mc_stream_push_codes(mc_stream* s, const int64_t* codes, int32_t n, int32_t 
     MC_CUDA(h, cudaMemcpy2DAsync(s->dev_codes_out, (size_t)new_len * 8, s->codes_ctx[dst], (size_t)cap * 8, (size_t)new_len * 8, C,
                                  cudaMemcpyDeviceToDevice, stream));
     MC_TRY(decode_impl(h, s->dev_codes_out, nullptr, C, new_len, keep, s->dev_wav_out, stream));
-    MC_CUDA(h, cudaMemcpyAsync(s->pin_wav, s->dev_wav_out, (size_t)C * keep * 4, cudaMemcpyDeviceToHost, stream));
+    if (emit) {
+      emit_chunk_kernel<<<1, POST_THREADS, 0, stream>>>(s->dev_wav_out, keep, s->emit_chunk, s->emit_fade, has_prev,
+                                                        s->emit_target_rms, s->emit_silence_thr, s->emit_fade_in,
+                                                        s->emit_prev_tail, s->emit_out);
+      MC_LAUNCH_CHECK(h, "emit_chunk_kernel");
+      MC_CUDA(h, cudaMemcpyAsync(s->pin_emit, s->emit_out, (size_t)emit_floats * 4, cudaMemcpyDeviceToHost, stream));
+    } else {
+      MC_CUDA(h, cudaMemcpyAsync(s->pin_wav, s->dev_wav_out, (size_t)C * keep * 4, cudaMemcpyDeviceToHost, stream));
+    }
     return MC_OK;
   };
-  MC_TRY(run_or_replay(s, std::make_tuple(1, old_len, n, keep, src), stream, body));
+  MC_TRY(run_or_replay(s, std::make_tuple(emit ? 2 + has_prev : 1, old_len, n, keep, src), stream, body));
   MC_CUDA(h, cudaStreamSynchronize(stream));
-  memcpy(wav_out, s->pin_wav, (size_t)C * keep * 4);
-  if (samples_out) *samples_out = keep;
+  if (emit) {
+    memcpy(wav_out, s->pin_emit, (size_t)emit_floats * 4);
+    if (samples_out) *samples_out = has_prev;
+    s->emit_has_prev = 1;
+  } else {
+    memcpy(wav_out, s->pin_wav, (size_t)C * keep * 4);
+    if (samples_out) *samples_out = keep;
+  }
   s->ccur = dst;
   s->code_len = new_len;
   return MC_OK;
+}
+
+int mc_stream_push_codes(mc_stream* s, const int64_t* codes, int32_t n, int32_t keep_samples, float* wav_out,
+                         int32_t* samples_out, mc_stream_t stream_) {
+  return stream_push_codes_impl(s, codes, n, keep_samples, false, wav_out, samples_out, stream_);
+}
+
+int mc_stream_set_emit(mc_stream* s, int32_t chunk_samples, int32_t fade_samples, float target_rms,
+                       float silence_rms_threshold, const float* fade_in) {
+  if (!s) return MC_ERR_ARG;
+  mc_handle* h = s->h;
+  MC_ENTER(h);
+  if (chunk_samples < 1 || fade_samples < 1 || fade_samples > chunk_samples || !fade_in)
+    return h->fail(MC_ERR_ARG, "mc_stream_set_emit: need 0 < fade (%d) <= chunk (%d) and a ramp", fade_samples, chunk_samples);
+  if (chunk_samples + fade_samples > s->cap_samples)
+    return h->fail(MC_ERR_ARG, "mc_stream_set_emit: chunk + fade exceeds the session capacity %d", s->cap_samples);
+  MC_CUDA(h, cudaStreamSynchronize(s->own));
+  stream_drop_graphs(s);   // the captured kernels carry the old parameters
+  if (s->emit_fade_in) cudaFree(s->emit_fade_in);
+  if (s->emit_prev_tail) cudaFree(s->emit_prev_tail);
+  if (s->emit_out) cudaFree(s->emit_out);
+  if (s->pin_emit) cudaFreeHost(s->pin_emit);
+  s->emit_fade_in = s->emit_prev_tail = s->emit_out = s->pin_emit = nullptr;
+  const size_t fb = (size_t)std::max(1, fade_samples) * 4, ob = (size_t)(2 * chunk_samples + fade_samples) * 4;
+  MC_CUDA(h, cudaMalloc(&s->emit_fade_in, fb));
+  MC_CUDA(h, cudaMalloc(&s->emit_prev_tail, fb));
+  MC_CUDA(h, cudaMalloc(&s->emit_out, ob));
+  MC_CUDA(h, cudaMallocHost(&s->pin_emit, ob));
+  if (fade_samples > 0) MC_CUDA(h, cudaMemcpy(s->emit_fade_in, fade_in, (size_t)fade_samples * 4, cudaMemcpyHostToDevice));
+  MC_CUDA(h, cudaMemset(s->emit_prev_tail, 0, fb));
+  s->emit_chunk = chunk_samples; s->emit_fade = fade_samples;
+  s->emit_target_rms = target_rms; s->emit_silence_thr = silence_rms_threshold;
+  s->emit_has_prev = 0;
+  return MC_OK;
+}
+
+int mc_stream_push_codes_emit(mc_stream* s, const int64_t* codes, int32_t n, float* out, int32_t* had_prev,
+                              mc_stream_t stream_) {
+  return stream_push_codes_impl(s, codes, n, 0, true, out, had_prev, stream_);
 }
 
 int mc_stream_set_graphs(mc_stream* s, int32_t enabled) {

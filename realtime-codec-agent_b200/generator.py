@@ -135,6 +135,12 @@ class StreamSession:
     def reset(self) -> None:
         self.gen._lib.mc_stream_reset(self._h)
 
+    def reset_audio(self) -> None:
+        self.gen._lib.mc_stream_reset_part(self._h, 1, 0)
+
+    def reset_codes(self) -> None:
+        self.gen._lib.mc_stream_reset_part(self._h, 0, 1)
+
     def set_graphs(self, enabled: bool) -> None:
         self.gen._lib.mc_stream_set_graphs(self._h, 1 if enabled else 0)
 
@@ -161,6 +167,28 @@ class StreamSession:
                                                 self.gen._stream())
         nat.check(self.gen._lib, self.gen._handle, rc, "mc_stream_push_codes")
         return out[: self.channels * got.value].reshape(self.channels, got.value)
+
+    def set_emit(self, chunk_samples: int, fade_samples: int, target_rms: float, silence_rms_threshold: float, fade_in) -> None:
+        """Arm the post-decode chain (mc_stream_set_emit); forgets the previous chunk."""
+        np = self._np
+        ramp = np.ascontiguousarray(fade_in, dtype=np.float32)
+        if ramp.shape != (fade_samples,):
+            raise ValueError("fade_in must hold fade_samples values")
+        rc = self.gen._lib.mc_stream_set_emit(self._h, chunk_samples, fade_samples, float(target_rms),
+                                              float(silence_rms_threshold), ramp.ctypes.data)
+        nat.check(self.gen._lib, self.gen._handle, rc, "mc_stream_set_emit")
+        self._emit_floats = 2 * chunk_samples + fade_samples
+
+    def push_codes_emit(self, codes):
+        """codes int64 [n] -> (float32 [2*chunk + fade] = emitted ++ cross-faded tail ++ new history chunk, had_prev)."""
+        np = self._np
+        codes = np.ascontiguousarray(codes, dtype=np.int64).reshape(-1)
+        out = np.empty((self._emit_floats,), dtype=np.float32)
+        had = C.c_int32(0)
+        rc = self.gen._lib.mc_stream_push_codes_emit(self._h, codes.ctypes.data, codes.shape[0], out.ctypes.data, C.byref(had),
+                                                     self.gen._stream())
+        nat.check(self.gen._lib, self.gen._handle, rc, "mc_stream_push_codes_emit")
+        return out, bool(had.value)
 
     def __del__(self):
         try:
@@ -351,6 +379,22 @@ class B200Generator:
         nat.check(self._lib, self._handle, rc, "mc_vq_search")
         return (codes, margin) if return_margin else codes
 
+    def embed_distance(self, ids: torch.Tensor, vocab_start: int = 0, ref: Optional[torch.Tensor] = None,
+                       want_mean: bool = False):
+        """ids int64 [rows,n] -> mean_j ||E[ids - vocab_start] - ref|| per row (fp32 [rows]) and, optionally,
+        the mean embedding per row (fp32 [rows,dq]) — external_tts_duplex_aligner.py:14-24 on the cached codebook."""
+        ids = ids.to(self.device, torch.int64).contiguous()
+        if ids.dim() == 1:
+            ids = ids[None]
+        rows, n = ids.shape
+        ref = None if ref is None else ref.to(self.device, F32).contiguous()
+        dist = torch.empty((rows,), dtype=F32, device=self.device)
+        mean = torch.empty((rows, self.spec.codebook_dim), dtype=F32, device=self.device) if want_mean else None
+        rc = self._lib.mc_embed_distance(self._handle, ids.data_ptr(), rows, n, int(vocab_start), nat.ptr(ref),
+                                         dist.data_ptr(), nat.ptr(mean), self._stream())
+        nat.check(self._lib, self._handle, rc, "mc_embed_distance")
+        return (dist, mean) if want_mean else dist
+
     # ---- the reference wrapper's call sequence (audio_tokenizer.py:190-192, 198-200)
     def pad_audio(self, x: torch.Tensor) -> torch.Tensor:
         return x                     # right padding to the hop multiple happens inside the first conv kernel
@@ -384,6 +428,22 @@ class B200Generator:
                                   rope_cols, rope_period, block_n, self._stream())
         nat.check(self._lib, self._handle, rc, "mc_op_gemm")
         return out
+
+    def op_emit_chunk(self, wav, chunk, fade, has_prev, target_rms, silence_thr, fade_in, prev_tail):
+        out = torch.empty((2 * chunk + fade,), dtype=F32, device=self.device)
+        rc = self._lib.mc_op_emit_chunk(self._handle, wav.data_ptr(), wav.numel(), chunk, fade, int(has_prev), float(target_rms),
+                                        float(silence_thr), fade_in.data_ptr(), prev_tail.data_ptr(), out.data_ptr(), self._stream())
+        nat.check(self._lib, self._handle, rc, "mc_op_emit_chunk")
+        return out
+
+    def op_embed_distance(self, table, ids, vocab_start=0, ref=None, want_mean=False):
+        rows, n = ids.shape
+        dist = torch.empty((rows,), dtype=F32, device=self.device)
+        mean = torch.empty((rows, 16), dtype=F32, device=self.device) if want_mean else None
+        rc = self._lib.mc_op_embed_distance(self._handle, table.data_ptr(), table.shape[0], ids.data_ptr(), rows, n,
+                                            int(vocab_start), nat.ptr(ref), dist.data_ptr(), nat.ptr(mean), self._stream())
+        nat.check(self._lib, self._handle, rc, "mc_op_embed_distance")
+        return (dist, mean) if want_mean else dist
 
     def op_rmsnorm(self, x, gamma):
         out = torch.empty(x.shape, dtype=BF16, device=self.device)
