@@ -147,7 +147,13 @@ int64_t mc_launch_count(const mc_handle* h);
  * the launch count.  Used by bench.py for the roofline object; off by default. */
 int mc_profile_begin(mc_handle* h);
 int mc_profile_end(mc_handle* h, double* ms, double* flops, double* bytes, int64_t* launches, int32_t n_classes);
-/* impl: 0 = tensor-core kernels (default), 1 = SIMT cross-check kernels for attention / VQ. */
+/* Engine options (all default to 1): "shared_stem" — overlapping hop-aligned windows of one mc_encode call share a
+ * single pass of the convolution stack (bit-identical results; 0 recomputes it per window, for A/B tests);
+ * "gemm_pair" — cta_group::2 GEMM where the shape allows. */
+int mc_set_option(mc_handle* h, const char* key, int32_t value);
+/* impl: 0 = tensor-core kernels (default), 1 = SIMT cross-check kernels for attention / VQ; attention also
+ * 2 = one-item-per-CTA tcgen05 kernel, 3 = two-slot persistent kernel without staged loads (A/B timing);
+ * attention_impl bit 2 forces the single-CTA GEMM. */
 int mc_set_debug_impl(mc_handle* h, int32_t attention_impl, int32_t vq_impl);
 
 /* ---- operator level (each is one kernel launch; used by the parity tests and profiling) ---- */

@@ -47,6 +47,7 @@ SYMBOLS = {
     "mc_codebook": (C.c_int, [_P, _P, _P]),
     "mc_launch_count": (_I64, [_P]),
     "mc_set_debug_impl": (C.c_int, [_P, _I32, _I32]),
+    "mc_set_option": (C.c_int, [_P, C.c_char_p, _I32]),
     "mc_profile_begin": (C.c_int, [_P]),
     "mc_profile_end": (C.c_int, [_P, _P, _P, _P, _P, _I32]),
     "mc_stream_create": (C.c_int, [_P, _I32, _I32, _I32, C.POINTER(_P)]),

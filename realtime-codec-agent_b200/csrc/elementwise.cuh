@@ -113,6 +113,24 @@ __global__ void compact_rows_kernel(const float4* __restrict__ x, float4* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// Shared convolution stem: x[b, t, :] = stem[b*fstep + t, :] for t in [pre, F) — the frames of window b
+// that do not depend on where the window starts, taken from the one pass over the whole span.
+// ---------------------------------------------------------------------------------------------
+__global__ void gather_stem_kernel(const float4* __restrict__ stem, float4* __restrict__ x, int B, int F, int pre,
+                                   int fstep, int d4) {
+  const int per = F - pre;
+  const long long total = static_cast<long long>(B) * per * d4;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % d4);
+    const long long row = idx / d4;
+    const int t = pre + static_cast<int>(row % per);
+    const long long b = row / per;
+    x[(b * F + t) * d4 + c] = __ldg(stem + (b * fstep + t) * d4 + c);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Code embedding: codes int64 [M] -> bf16 [M, 64] = (projected codebook row, zero padded to the
 // 64-wide K block of the decoder's input projection).  One thread = one 16-byte store.
 // ---------------------------------------------------------------------------------------------

@@ -152,6 +152,10 @@ int launch_attention(mc_handle* h, const bf16* qkv, bf16* out, int B, int F, int
   McProfScope prof(h, 1, 4.0 * B * out_rows * span * s.d_model,
                    (double)B * (F * 2.0 + out_rows * 2.0) * s.d_model * 2.0, stream);
   if (impl == 0 && attn_sm100_supported(s.window_left, s.window_right)) {
+    MC_TRY(launch_attention_sm100_v3(h, qkv, out, B, F, out_rows, stream));
+    return MC_OK;
+  }
+  if (impl == 3 && attn_sm100_supported(s.window_left, s.window_right)) {   // previous two-slot version (A/B timing)
     MC_TRY(launch_attention_sm100_v2(h, qkv, out, B, F, out_rows, stream));
     return MC_OK;
   }
@@ -276,6 +280,95 @@ int launch_vq(mc_handle* h, const float* z, int n_items, int F, int keep, int64_
 size_t vq_scratch_bytes(mc_handle* h, int Mq);
 
 // ----------------------------------------------------------------- encode
+// Encoder conv stack over Bc items of Tc samples (item b at wav + b*ld; samples >= Tc read as zero): conv0 on CUDA
+// cores, the rest as implicit GEMMs.  The last conv writes fp32 rows [Tc/hop, d] per item at x_out + b*x_item_stride.
+struct ConvPlan {
+  int B = 0, T = 0;
+  std::vector<int> Tl;          // output length of every conv
+  std::vector<size_t> off;      // workspace offset of the (left-padded) bf16 output of conv i, i < n-1
+};
+
+ConvPlan plan_conv(const mc_spec& s, Carver& cv, int Bc, int Tc_padded) {
+  ConvPlan p;
+  p.B = Bc; p.T = Tc_padded;
+  const int n = s.n_convs;
+  p.Tl.resize(n); p.off.resize(n);
+  int t = Tc_padded;
+  for (int i = 0; i < n; ++i) { t /= s.conv_strides[i]; p.Tl[i] = t; }
+  for (int i = 0; i + 1 < n; ++i)
+    p.off[i] = cv.take((size_t)Bc * (s.conv_strides[i + 1] + p.Tl[i]) * s.conv_channels[i] * 2 + 65536);
+  return p;
+}
+
+int run_conv_stack(mc_handle* h, const ConvPlan& cp, uint8_t* base, const float* wav, int64_t ld, int Tvalid,
+                   float* x_out, int64_t x_item_stride, cudaStream_t stream) {
+  const mc_spec& s = h->spec;
+  const int n = s.n_convs, d = s.d_model, B = cp.B;
+  const std::vector<int>& Tl = cp.Tl;
+  const int* Cl = s.conv_channels;
+  for (int i = 0; i + 1 < n; ++i) {  // zero the left padding of every conv input
+    const int pad = s.conv_strides[i + 1];
+    const size_t pitch = (size_t)(pad + Tl[i]) * Cl[i] * 2;
+    MC_CUDA(h, cudaMemset2DAsync(base + cp.off[i], pitch, 0, (size_t)pad * Cl[i] * 2, B, stream));
+  }
+  {
+    const int s0 = s.conv_strides[0], C0 = Cl[0];
+    const int cgroups = C0 / 8;
+    if ((2 * s0 != 8 && 2 * s0 != 16) || C0 % 8 != 0 || 256 % cgroups != 0)
+      return h->fail(MC_ERR_ARG, "conv0: stride %d / channels %d unsupported", s0, C0);
+    const int threads = 256;
+    const long long frames = (long long)B * Tl[0];
+    const int grid = ew_grid(h, frames * cgroups, threads);
+    McProfScope prof(h, 3, 2.0 * B * Tl[0] * 2 * s0 * C0, (double)B * Tvalid * 4.0 + (double)B * Tl[0] * C0 * 2.0, stream);
+    bf16* o0 = reinterpret_cast<bf16*>(base + cp.off[0]);
+    if (2 * s0 == 8)
+      conv_first_kernel<8><<<grid, threads, 0, stream>>>(wav, ld, Tvalid, B, Tl[0], s0, C0, h->ptr<float>("enc.conv0.w"),
+                                                          h->ptr<float>("enc.conv0.b"), o0, s.conv_strides[1]);
+    else
+      conv_first_kernel<16><<<grid, threads, 0, stream>>>(wav, ld, Tvalid, B, Tl[0], s0, C0, h->ptr<float>("enc.conv0.w"),
+                                                           h->ptr<float>("enc.conv0.b"), o0, s.conv_strides[1]);
+    MC_LAUNCH_CHECK(h, "conv_first_kernel");
+  }
+  for (int i = 1; i < n; ++i) {
+    const int si = s.conv_strides[i];
+    const long long rows = (long long)B * (1 + Tl[i]);
+    if (rows > INT_MAX) return h->fail(MC_ERR_ARG, "encode: conv %d has too many rows", i);
+    GemmCall g{};
+    g.A = reinterpret_cast<const bf16*>(base + cp.off[i - 1]);
+    g.a_k_wrap = si * Cl[i - 1];
+    g.a_rows = rows;
+    g.W = h->ptr<bf16>("enc.conv" + std::to_string(i) + ".w");
+    g.bias = h->ptr<float>("enc.conv" + std::to_string(i) + ".b");
+    g.M = (int)rows; g.N = Cl[i]; g.K = 2 * g.a_k_wrap;
+    g.grp_in = 1 + Tl[i]; g.grp_valid = Tl[i];
+    if (i + 1 < n) {
+      const int pad = s.conv_strides[i + 1];
+      g.act = ACT_GELU_TANH; g.out_mode = OUT_BF16; g.out = base + cp.off[i]; g.ldo = Cl[i];
+      g.grp_stride = (int64_t)(pad + Tl[i]) * Cl[i]; g.grp_off = (int64_t)pad * Cl[i];
+    } else {
+      g.act = ACT_NONE; g.out_mode = OUT_F32; g.out = x_out; g.ldo = d;
+      g.grp_stride = x_item_stride; g.grp_off = 0;
+    }
+    MC_TRY(launch_gemm(h, g, stream));
+  }
+  return MC_OK;
+}
+
+// Frames of the conv stem whose value can depend on where a window starts: the causal convs see zeros
+// instead of real history only through a chain of "first output" positions, which ends after frame 1
+// (checked layer by layer for the strides in the spec; see DESIGN.md §4 "shared convolution stem").
+int stem_prefix_frames(const mc_spec& s) {
+  // a conv output at position v is window-specific iff one of its inputs [v*st - st, v*st + st) is padding or
+  // window-specific; `dirty` = number of leading window-specific positions at the current level
+  long long dirty = 0;   // raw samples: none are window-specific, only the padding is
+  for (int i = 0; i < s.n_convs; ++i) {
+    const int st = s.conv_strides[i];
+    // position v reads inputs up to... it is clean iff v*st - st >= dirty  <=>  v >= dirty/st + 1 (ceil)
+    dirty = (dirty + st - 1) / st + 1;
+  }
+  return (int)dirty;
+}
+
 int encode_impl(mc_handle* h, const float* wav, int64_t ld, int B, int T, int keep, int64_t* codes, float* margin,
                 float* z_e_out, cudaStream_t stream) {
   const mc_spec& s = h->spec;
@@ -292,17 +385,26 @@ int encode_impl(mc_handle* h, const float* wav, int64_t ld, int B, int T, int ke
   if (Mll * std::max(3 * d, s.ffn_dim) > (long long)INT_MAX) return h->fail(MC_ERR_ARG, "encode: batch too large");
   const int M = (int)Mll;
 
-  // per-layer time lengths and channel counts
-  std::vector<int> Tl(n), Cl(n);
-  {
-    int t = Tp;
-    for (int i = 0; i < n; ++i) { t /= s.conv_strides[i]; Tl[i] = t; Cl[i] = s.conv_channels[i]; }
-  }
-  // ---- carve workspace (two passes: size, then pointers)
-  std::vector<size_t> conv_off(n);
+  // Shared convolution stem (exact): overlapping windows whose starts are hop-aligned see identical conv
+  // outputs from frame `pre` on, so the stack runs ONCE over the whole span and per window only over the
+  // first `pre` frames; the windows' residual streams are then gathered from the span's frames.
+  const int pre = stem_prefix_frames(s);
+  const long long span_samples = (long long)(B - 1) * ld + T;
+  const long long span_frames = span_samples / hop;
+  const bool shared = h->shared_stem && B >= 2 && ld > 0 && ld < T && ld % hop == 0 && T % hop == 0 && F > pre &&
+                      span_samples <= INT_MAX && span_frames + (long long)pre * B < (long long)B * F / 2;
+
+  // ---- carve workspace (sizes first, then pointers)
   Carver cv;
-  for (int i = 0; i + 1 < n; ++i)
-    conv_off[i] = cv.take((size_t)B * (s.conv_strides[i + 1] + Tl[i]) * Cl[i] * 2 + 65536);
+  ConvPlan cp_full, cp_span, cp_pre;
+  size_t ostem = 0;
+  if (shared) {
+    cp_span = plan_conv(s, cv, 1, (int)span_samples);
+    cp_pre = plan_conv(s, cv, B, pre * hop);
+    ostem = cv.take((size_t)span_frames * d * 4);
+  } else {
+    cp_full = plan_conv(s, cv, B, Tp);
+  }
   Carver cv2 = cv;
   carve_stack(cv2, nullptr, M, d, s.ffn_dim, true);
   size_t oz = cv2.take((size_t)M * dq * 4);
@@ -313,49 +415,19 @@ int encode_impl(mc_handle* h, const float* wav, int64_t ld, int B, int T, int ke
   float* z_e = reinterpret_cast<float*>(base + oz);
   void* vq_scratch = base + ovq;
 
-  // ---- conv stack
-  for (int i = 0; i + 1 < n; ++i) {  // zero the left padding of every conv input
-    const int pad = s.conv_strides[i + 1];
-    const size_t pitch = (size_t)(pad + Tl[i]) * Cl[i] * 2;
-    MC_CUDA(h, cudaMemset2DAsync(base + conv_off[i], pitch, 0, (size_t)pad * Cl[i] * 2, B, stream));
-  }
-  {
-    const int s0 = s.conv_strides[0], C0 = Cl[0];
-    const int cgroups = C0 / 8;
-    if ((2 * s0 != 8 && 2 * s0 != 16) || C0 % 8 != 0 || 256 % cgroups != 0)
-      return h->fail(MC_ERR_ARG, "conv0: stride %d / channels %d unsupported", s0, C0);
-    const int threads = 256;
-    const long long frames = (long long)B * Tl[0];
-    const int grid = ew_grid(h, frames * cgroups, threads);
-    McProfScope prof(h, 3, 2.0 * B * Tl[0] * 2 * s0 * C0, (double)B * T * 4.0 + (double)B * Tl[0] * C0 * 2.0, stream);
-    bf16* o0 = reinterpret_cast<bf16*>(base + conv_off[0]);
-    if (2 * s0 == 8)
-      conv_first_kernel<8><<<grid, threads, 0, stream>>>(wav, ld, T, B, Tl[0], s0, C0, h->ptr<float>("enc.conv0.w"),
-                                                          h->ptr<float>("enc.conv0.b"), o0, s.conv_strides[1]);
-    else
-      conv_first_kernel<16><<<grid, threads, 0, stream>>>(wav, ld, T, B, Tl[0], s0, C0, h->ptr<float>("enc.conv0.w"),
-                                                           h->ptr<float>("enc.conv0.b"), o0, s.conv_strides[1]);
-    MC_LAUNCH_CHECK(h, "conv_first_kernel");
-  }
-  for (int i = 1; i < n; ++i) {
-    const int si = s.conv_strides[i];
-    GemmCall g{};
-    g.A = reinterpret_cast<const bf16*>(base + conv_off[i - 1]);
-    g.a_k_wrap = si * Cl[i - 1];
-    g.a_rows = (int64_t)B * (1 + Tl[i]);
-    g.W = h->ptr<bf16>("enc.conv" + std::to_string(i) + ".w");
-    g.bias = h->ptr<float>("enc.conv" + std::to_string(i) + ".b");
-    g.M = B * (1 + Tl[i]); g.N = Cl[i]; g.K = 2 * g.a_k_wrap;
-    g.grp_in = 1 + Tl[i]; g.grp_valid = Tl[i];
-    if (i + 1 < n) {
-      const int pad = s.conv_strides[i + 1];
-      g.act = ACT_GELU_TANH; g.out_mode = OUT_BF16; g.out = base + conv_off[i]; g.ldo = Cl[i];
-      g.grp_stride = (int64_t)(pad + Tl[i]) * Cl[i]; g.grp_off = (int64_t)pad * Cl[i];
-    } else {
-      g.act = ACT_NONE; g.out_mode = OUT_F32; g.out = sb.x; g.ldo = d;
-      g.grp_stride = (int64_t)F * d; g.grp_off = 0;
-    }
-    MC_TRY(launch_gemm(h, g, stream));
+  // ---- conv stack -> fp32 residual stream sb.x [B*F, d]
+  if (shared) {
+    float* stem = reinterpret_cast<float*>(base + ostem);
+    MC_TRY(run_conv_stack(h, cp_span, base, wav, span_samples, (int)span_samples, stem, 0, stream));
+    MC_TRY(run_conv_stack(h, cp_pre, base, wav, ld, pre * hop, sb.x, (int64_t)F * d, stream));
+    const long long items = (long long)B * (F - pre) * (d / 4);
+    McProfScope prof(h, 3, 0.0, (double)B * (F - pre) * d * 8.0, stream);
+    gather_stem_kernel<<<ew_grid(h, items, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(stem),
+                                                                 reinterpret_cast<float4*>(sb.x), B, F, pre,
+                                                                 (int)(ld / hop), d / 4);
+    MC_LAUNCH_CHECK(h, "gather_stem_kernel");
+  } else {
+    MC_TRY(run_conv_stack(h, cp_full, base, wav, ld, T, sb.x, (int64_t)F * d, stream));
   }
   // ---- transformer (only the rows the kept frames depend on, unless the full latents are requested)
   const int keep_rows = z_e_out ? F : keep;
@@ -664,6 +736,15 @@ int mc_profile_end(mc_handle* h, double* ms, double* flops, double* bytes, int64
     h->event_pool.push_back(r.a); h->event_pool.push_back(r.b);
   }
   h->prof.clear();
+  return MC_OK;
+}
+
+int mc_set_option(mc_handle* h, const char* key, int32_t value) {
+  if (!h || !key) return MC_ERR_ARG;
+  const std::string k(key);
+  if (k == "shared_stem") h->shared_stem = value != 0;
+  else if (k == "gemm_pair") h->gemm_pair = value != 0;
+  else return h->fail(MC_ERR_ARG, "mc_set_option: unknown option '%s'", key);
   return MC_OK;
 }
 

@@ -309,6 +309,9 @@ class B200Generator:
     def set_debug_impl(self, attention: int = 0, vq: int = 0) -> None:
         nat.check(self._lib, self._handle, self._lib.mc_set_debug_impl(self._handle, attention, vq), "mc_set_debug_impl")
 
+    def set_option(self, key: str, value: int) -> None:
+        nat.check(self._lib, self._handle, self._lib.mc_set_option(self._handle, key.encode(), int(value)), "mc_set_option")
+
     PROFILE_CLASSES = ("gemm", "attention", "vq", "elementwise")
 
     def profile_begin(self) -> None:

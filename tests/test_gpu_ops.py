@@ -131,7 +131,7 @@ def test_rmsnorm(gen):
     assert (out.float() - ref).abs().max().item() < 0.03
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 @pytest.mark.parametrize("B,Fr", [(1, 100), (3, 100), (2, 37), (1, 128), (2, 300), (40, 100)])
 def test_window_attention(gen, impl, B, Fr):
     d, H = gen.spec.d_model, gen.spec.n_heads
@@ -146,6 +146,17 @@ def test_window_attention(gen, impl, B, Fr):
     ref = ref.transpose(1, 2).reshape(B * Fr, d)
     err = (out.float() - ref).abs().max().item()
     assert err < 0.03, f"impl {impl}: max abs err {err}"
+
+
+@pytest.mark.parametrize("B,Fr", [(1, 100), (5, 100), (300, 100), (2, 128), (3, 129), (2, 300), (1, 7)])
+def test_attention_v3_is_bit_identical_to_v2(gen, B, Fr):
+    """The staged-load kernel (impl 0) changes scheduling only: same masks, same ex2, same key-group sums."""
+    d = gen.spec.d_model
+    qkv = _rand((B * Fr, 3 * d), seed=19).to(torch.bfloat16)
+    a = gen.op_attention(qkv, B, Fr, impl=0)
+    b = gen.op_attention(qkv, B, Fr, impl=3)
+    assert torch.equal(a, b)
+    assert torch.equal(a, gen.op_attention(qkv, B, Fr, impl=0))
 
 
 @pytest.mark.parametrize("impl", [0, 1])

@@ -124,6 +124,35 @@ def test_batching_windows_and_keep_last_are_exact(bundle):
     assert gen.encode(wav[None, : 320 * 7 + 1]).shape == (1, 8)
 
 
+@pytest.mark.parametrize("ld,T,B", [(1600, 32000, 24), (320, 32000, 9), (640, 6400, 30), (3200, 32000, 3), (1600, 1600 * 3, 7)])
+def test_shared_conv_stem_is_exact(bundle, ld, T, B):
+    """Overlapping hop-aligned windows share ONE pass of the conv stack (frames >= 2 of a window do not depend on
+    where it starts); latents and codes must be bit-identical to recomputing the stack per window."""
+    name, spec, w, g, gen = bundle
+    wav = torch.from_numpy(np.concatenate([g["wav0"], g["wav1"]])).cuda()
+    assert (B - 1) * ld + T <= wav.numel()
+    try:
+        gen.set_option("shared_stem", 1)
+        c1, m1, z1 = gen.encode(wav, row_stride=ld, num_windows=B, window_samples=T, return_margin=True, return_latents=True)
+        k1 = gen.encode(wav, row_stride=ld, num_windows=B, window_samples=T, keep_last_frames=5)
+        gen.set_option("shared_stem", 0)
+        c0, m0, z0 = gen.encode(wav, row_stride=ld, num_windows=B, window_samples=T, return_margin=True, return_latents=True)
+    finally:
+        gen.set_option("shared_stem", 1)
+    assert torch.equal(z1, z0) and torch.equal(c1, c0) and torch.equal(m1, m0)
+    assert torch.equal(k1, c0[:, -5:])
+    mat = torch.stack([wav[b * ld: b * ld + T] for b in range(B)])          # materialised windows: never shared
+    assert torch.equal(gen.encode(mat), c0)
+
+
+def test_unaligned_window_stride_falls_back(bundle):
+    name, spec, w, g, gen = bundle
+    wav = torch.from_numpy(g["wav0"]).cuda()
+    a = gen.encode(wav, row_stride=1000, num_windows=6, window_samples=32000)
+    mat = torch.stack([wav[b * 1000: b * 1000 + 32000] for b in range(6)])
+    assert torch.equal(a, gen.encode(mat))
+
+
 def test_reference_call_sequence_on_the_duck_type(bundle):
     """The exact attribute/method sequence of audio_tokenizer.py:189-201 and :158 on B200Generator."""
     name, spec, w, g, gen = bundle

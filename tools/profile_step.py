@@ -1,5 +1,6 @@
-"""One batch of the bench workload (256 windows x 2.0 s, keep 5 frames) run twice: the command ncu wraps.
-Also prints per-class device time from the engine's own event profile."""
+"""One batch of the bench workload (B windows x 2.0 s read through the overlapping view, keep 5 frames): per-class
+device time from the engine's own event profile, A/B over the engine options.  `profile_step.py B 1` runs only the
+default configuration twice (the command the ncu launch list wraps)."""
 import os
 import sys
 
@@ -11,21 +12,45 @@ import realtime_codec_agent_b200 as pkg
 
 spec = pkg.DEFAULT_SPEC
 gen = pkg.B200Generator(spec, pkg.init_random_weights(spec, seed=0), device="cuda")
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+only_default = len(sys.argv) > 2 and sys.argv[2] == "1"
 wav = pkg.synth_audio(B * 1600 + 32000, device="cuda")
-for it in range(2):
-    gen.profile_begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    codes = gen.encode(wav, keep_last_frames=5, row_stride=1600, num_windows=B, window_samples=32000)
-    e1.record()
-    torch.cuda.synchronize()
-    prof = gen.profile_end()
-    print(f"iter {it}: {e0.elapsed_time(e1):.3f} ms for {B} windows; " +
-          "; ".join(f"{k}: {v['ms']:.3f} ms / {v['launches']} launches" + (f" / {v['flops'] / v['ms'] / 1e9:.0f} TFLOP/s" if v['flops'] and v['ms'] else "")
-                    for k, v in prof.items()))
-print("checksum", int(codes.sum()), "audio_hash", float(wav.double().sum()), float(wav.double().abs().sum()))
+
+
+def run(tag, iters=3):
+    best = None
+    for it in range(iters):
+        gen.profile_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        codes = gen.encode(wav, keep_last_frames=5, row_stride=1600, num_windows=B, window_samples=32000)
+        e1.record()
+        torch.cuda.synchronize()
+        prof = gen.profile_end()
+        ms = e0.elapsed_time(e1)
+        line = (f"[{tag}] iter {it}: {ms:.3f} ms for {B} windows ({B * 0.1 / ms * 1e3:.0f} audio-s/s); " +
+                "; ".join(f"{k}: {v['ms']:.3f} ms / {v['launches']} launches" +
+                          (f" / {v['flops'] / v['ms'] / 1e9:.0f} TFLOP/s" if v['flops'] and v['ms'] else "") +
+                          (f" / {v['bytes'] / v['ms'] / 1e6:.0f} GB/s" if k == "elementwise" and v['ms'] else "")
+                          for k, v in prof.items()))
+        if best is None or ms < best[0]:
+            best = (ms, line)
+    print(best[1])
+    return codes
+
+
+codes = run("default")
+if only_default:
+    run("default")
+else:
+    gen.set_debug_impl(attention=3)
+    c2 = run("attention v2 (no staged loads)")
+    gen.set_debug_impl(attention=0)
+    gen.set_option("shared_stem", 0)
+    c3 = run("conv stack per window (shared_stem=0)")
+    gen.set_option("shared_stem", 1)
+    print("attention v3 == v2:", bool(torch.equal(codes, c2)), " shared stem == per-window:", bool(torch.equal(codes, c3)))
+print("checksum", int(codes.sum()), "audio_hash", float(wav.double().sum()))
 again = gen.encode(wav, keep_last_frames=5, row_stride=1600, num_windows=B, window_samples=32000)
-full = gen.encode(wav, keep_last_frames=0, row_stride=1600, num_windows=B, window_samples=32000)
-print("repeat_equal", bool(torch.equal(codes, again)), "full_vs_keep5_equal", bool(torch.equal(full[:, -5:], codes)),
-      "n_diff", int((full[:, -5:] != codes).sum()))
+full = gen.encode(wav[: 256 * 1600 + 32000], keep_last_frames=0, row_stride=1600, num_windows=256, window_samples=32000)
+print("repeat_equal", bool(torch.equal(codes, again)), "full_vs_keep5_equal", bool(torch.equal(full[:, -5:], codes[:256])))
