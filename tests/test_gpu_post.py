@@ -4,7 +4,7 @@ and the fused push_codes_emit call against the oracle chain fed with the engine'
 
 Tolerances: with target_volume_rms = 0 (the reference default, realtime_agent_config.py:25) the chain is
 multiplies and adds with numpy's roundings -> BIT-EXACT.  With RMS normalisation the gain comes from an fp64
-device sum vs numpy's fp32 pairwise sum: relative 2e-6.  Aligner scores: relative 1e-5 (fp32 norms, fp64 means).
+device sum vs numpy's fp32 pairwise sum: relative 2e-6 (absolute 1e-7 where the crossfade cancels).  Aligner scores: relative 1e-5 (fp32 norms, fp64 means).
 """
 import os
 
@@ -18,6 +18,7 @@ from oracle import post_decode_oracle as po
 pytestmark = pytest.mark.gpu
 SR, CHUNK, L = 16000, 1600, 320
 RMS_RTOL = 2e-6
+RMS_ATOL = 1e-7      # cross-faded samples are sums of two products and may cancel; 1e-7 is -140 dB re full scale
 
 
 @pytest.fixture(scope="module")
@@ -44,7 +45,7 @@ def test_emit_kernel_replays_reference_golden(g, gen, tag, target):
         if target == 0.0:
             assert np.array_equal(emitted, want), f"chunk {i}"
         else:
-            assert np.allclose(emitted, want, rtol=RMS_RTOL, atol=1e-9), f"chunk {i}"
+            assert np.allclose(emitted, want, rtol=RMS_RTOL, atol=RMS_ATOL), f"chunk {i}"
         if i > 0:
             history[-1] = np.concatenate((history[-1][:CHUNK - L], cross))
         history.append(fresh)
@@ -52,7 +53,7 @@ def test_emit_kernel_replays_reference_golden(g, gen, tag, target):
     if target == 0.0:
         assert np.array_equal(hist, g[f"chain_history_{tag}"])
     else:
-        assert np.allclose(hist, g[f"chain_history_{tag}"], rtol=RMS_RTOL, atol=1e-9)
+        assert np.allclose(hist, g[f"chain_history_{tag}"], rtol=RMS_RTOL, atol=RMS_ATOL)
 
 
 def test_embed_distance_kernel_replays_reference_golden(g, gen):
@@ -83,14 +84,14 @@ def test_fused_emit_call_equals_oracle_chain_on_engine_output(gen, target):
         if target == 0.0:
             assert np.array_equal(got, want), f"chunk {i // 5}"
         else:
-            assert np.allclose(got, want, rtol=RMS_RTOL, atol=1e-9), f"chunk {i // 5}"
+            assert np.allclose(got, want, rtol=RMS_RTOL, atol=RMS_ATOL), f"chunk {i // 5}"
     a, b = np.concatenate(emitter.audio_history_ch1), np.concatenate(chain.history)
-    assert a.shape == b.shape and np.allclose(a, b, rtol=RMS_RTOL if target else 0.0, atol=1e-9 if target else 0.0)
+    assert a.shape == b.shape and np.allclose(a, b, rtol=RMS_RTOL if target else 0.0, atol=RMS_ATOL if target else 0.0)
     assert tok_a.detokenize_context == tok_b.detokenize_context
     # reset -> first-chunk behaviour again
     emitter.reset(); tok_a.reset_context()
     chain.history = []; tok_b.reset_context()
-    assert np.allclose(emitter.emit(s[:5]), chain.step(s[:5]), rtol=RMS_RTOL, atol=1e-9)
+    assert np.allclose(emitter.emit(s[:5]), chain.step(s[:5]), rtol=RMS_RTOL, atol=RMS_ATOL)
 
 
 def test_native_aligner_matches_oracle_on_engine_codebook(gen):
