@@ -149,7 +149,8 @@ int mc_profile_begin(mc_handle* h);
 int mc_profile_end(mc_handle* h, double* ms, double* flops, double* bytes, int64_t* launches, int32_t n_classes);
 /* Engine options (all default to 1): "shared_stem" — overlapping hop-aligned windows of one mc_encode call share a
  * single pass of the convolution stack (bit-identical results; 0 recomputes it per window, for A/B tests);
- * "gemm_pair" — cta_group::2 GEMM where the shape allows. */
+ * "gemm_pair" — cta_group::2 GEMM where the shape allows; "fast_epilogue" — its mode-specialised epilogues
+ * (bit-identical to the generic one). */
 int mc_set_option(mc_handle* h, const char* key, int32_t value);
 /* impl: 0 = tensor-core kernels (default), 1 = SIMT cross-check kernels for attention / VQ; attention also
  * 2 = one-item-per-CTA tcgen05 kernel, 3 = two-slot persistent kernel without staged loads (A/B timing);

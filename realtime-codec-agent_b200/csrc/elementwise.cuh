@@ -96,6 +96,43 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restr
   }
 }
 
+// Register-resident variant for d = NV * 128: a lane keeps its NV float4 of the row, so x is read from HBM exactly
+// once (all NV loads in flight together) and the statistics and the scaling both come from registers.  Summation
+// order as in rmsnorm_kernel (per-lane partial sums over i = lane, lane+32, ..., then the xor tree).
+template <int NV>
+__global__ void __launch_bounds__(256)
+rmsnorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ out, int M,
+                    float eps, int grp_in, long long grp_stride, long long grp_off) {
+  constexpr int d = NV * 128;
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  float4 g[NV];
+#pragma unroll
+  for (int u = 0; u < NV; ++u) g[u] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * u);
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * d);
+    float4 v[NV];
+#pragma unroll
+    for (int u = 0; u < NV; ++u) v[u] = xr[lane + 32 * u];
+    float ss = 0.0f;
+#pragma unroll
+    for (int u = 0; u < NV; ++u) ss += v[u].x * v[u].x + v[u].y * v[u].y + v[u].z * v[u].z + v[u].w * v[u].w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = rsqrtf(ss / static_cast<float>(d) + eps);
+    const int grp = row / grp_in;
+    const long long obase = static_cast<long long>(grp) * grp_stride + grp_off + static_cast<long long>(row - grp * grp_in) * d;
+    uint2* orow_p = reinterpret_cast<uint2*>(out + obase);
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      uint2 o;
+      o.x = pack_bf16x2(v[u].x * inv * g[u].x, v[u].y * inv * g[u].y);
+      o.y = pack_bf16x2(v[u].z * inv * g[u].z, v[u].w * inv * g[u].w);
+      orow_p[lane + 32 * u] = o;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Keep the last r_out of r_in fp32 rows of every window (dead-output elimination between layers).
 // ---------------------------------------------------------------------------------------------

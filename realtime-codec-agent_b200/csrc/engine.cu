@@ -63,6 +63,21 @@ int launch_gemm_bn(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
 }
 
 // CTA-pair kernel: 256 x 256 tiles on 74 clusters of two CTAs
+template <int EPI>
+int launch_gemm_pair_epi(mc_handle* h, const GemmCall& c, const GemmParams& p, const CUtensorMap* ma, const CUtensorMap* mb,
+                         const CUtensorMap* mo, int pairs, cudaStream_t stream) {
+  constexpr int BN = 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MC_CUDA(h, cudaFuncSetAttribute(gemm2_bf16_sm100_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Gemm2Cfg<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  gemm2_bf16_sm100_kernel<BN, EPI><<<2 * pairs, GEMM_THREADS, Gemm2Cfg<BN>::kSmemBytes, stream>>>(*ma, *mb, *mo, p);
+  MC_LAUNCH_CHECK(h, "gemm2_bf16_sm100_kernel");
+  return MC_OK;
+}
+
 int launch_gemm_pair(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   constexpr int BN = 256;
   const CUtensorMap *ma, *mb;
@@ -83,20 +98,20 @@ int launch_gemm_pair(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   p.rope_ld = h->spec.max_positions;
   p.rope_cos = c.rope_period > 0 ? h->ptr<float>("rope.cos") : nullptr;
   p.rope_sin = c.rope_period > 0 ? h->ptr<float>("rope.sin") : nullptr;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MC_CUDA(h, cudaFuncSetAttribute(gemm2_bf16_sm100_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Gemm2Cfg<BN>::kSmemBytes));
-    attr_set = true;
-  }
   const int m_tiles = (c.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM), n_tiles = (c.N + BN - 1) / BN;
   const int pairs = std::min(m_tiles * n_tiles, h->num_sms / 2);
   const double valid_rows = c.grp_in == INT_MAX ? (double)c.M : (double)c.M / c.grp_in * c.grp_valid;
   const double out_bytes = valid_rows * c.N * (c.out_mode == OUT_BF16 ? 2.0 : (c.out_mode == OUT_F32 ? 4.0 : 8.0));
   McProfScope prof(h, 0, 2.0 * valid_rows * c.N * c.K, valid_rows * c.a_k_wrap * 2.0 + (double)c.N * c.K * 2.0 + out_bytes, stream);
-  gemm2_bf16_sm100_kernel<BN><<<2 * pairs, GEMM_THREADS, Gemm2Cfg<BN>::kSmemBytes, stream>>>(*ma, *mb, *mo, p);
-  MC_LAUNCH_CHECK(h, "gemm2_bf16_sm100_kernel");
-  return MC_OK;
+  // specialised epilogues (gemm_sm100.cuh): TMA-store output, bias, whole 256-column tiles, rope on 64-wide heads
+  const bool fast_ok = h->fast_epilogue && tma_out && c.bias != nullptr && c.N % BN == 0;
+  if (fast_ok && c.out_mode == OUT_BF16 && c.act == ACT_NONE && c.rope_period > 0 && c.rope_cols % 64 == 0)
+    return launch_gemm_pair_epi<EPI_ROPE_BF16>(h, c, p, ma, mb, mo, pairs, stream);
+  if (fast_ok && c.out_mode == OUT_BF16 && c.act == ACT_GELU_TANH && c.rope_period == 0)
+    return launch_gemm_pair_epi<EPI_GELU_BF16>(h, c, p, ma, mb, mo, pairs, stream);
+  if (fast_ok && c.out_mode == OUT_F32_RESIDUAL && c.act == ACT_NONE && c.rope_period == 0)
+    return launch_gemm_pair_epi<EPI_RESID_F32>(h, c, p, ma, mb, mo, pairs, stream);
+  return launch_gemm_pair_epi<EPI_GENERIC>(h, c, p, ma, mb, mo, pairs, stream);
 }
 
 int launch_gemm(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
@@ -140,7 +155,14 @@ int launch_rmsnorm(mc_handle* h, const float* x, const float* gamma, bf16* out, 
   const int warps = 8;
   const int grid = ew_grid(h, M, warps);
   McProfScope prof(h, 3, 0.0, (double)M * d * 6.0, stream);
-  rmsnorm_kernel<<<grid, warps * 32, 0, stream>>>(x, gamma, out, M, d, h->spec.norm_eps, grp_in, grp_stride, grp_off);
+  const float eps = h->spec.norm_eps;
+  switch (d % 128 == 0 ? d / 128 : 0) {   // register-resident rows (x read once) for the widths in use
+    case 1: rmsnorm_rows_kernel<1><<<grid, warps * 32, 0, stream>>>(x, gamma, out, M, eps, grp_in, grp_stride, grp_off); break;
+    case 2: rmsnorm_rows_kernel<2><<<grid, warps * 32, 0, stream>>>(x, gamma, out, M, eps, grp_in, grp_stride, grp_off); break;
+    case 4: rmsnorm_rows_kernel<4><<<grid, warps * 32, 0, stream>>>(x, gamma, out, M, eps, grp_in, grp_stride, grp_off); break;
+    case 8: rmsnorm_rows_kernel<8><<<grid, warps * 32, 0, stream>>>(x, gamma, out, M, eps, grp_in, grp_stride, grp_off); break;
+    default: rmsnorm_kernel<<<grid, warps * 32, 0, stream>>>(x, gamma, out, M, d, eps, grp_in, grp_stride, grp_off);
+  }
   MC_LAUNCH_CHECK(h, "rmsnorm_kernel");
   return MC_OK;
 }
@@ -744,6 +766,7 @@ int mc_set_option(mc_handle* h, const char* key, int32_t value) {
   const std::string k(key);
   if (k == "shared_stem") h->shared_stem = value != 0;
   else if (k == "gemm_pair") h->gemm_pair = value != 0;
+  else if (k == "fast_epilogue") h->fast_epilogue = value != 0;
   else return h->fail(MC_ERR_ARG, "mc_set_option: unknown option '%s'", key);
   return MC_OK;
 }

@@ -59,6 +59,7 @@ struct mc_handle {
   int64_t launches = 0;
   int attn_impl = 0, vq_impl = 0;
   int gemm_pair = 1;  // use the cta_group::2 GEMM where the shape allows
+  bool fast_epilogue = true;  // mode-specialised, software-pipelined epilogues in the CTA-pair GEMM
   bool shared_stem = true;  // overlapping hop-aligned windows share one pass of the conv stack (exact)
   // optional per-class device timing (bench.py's roofline): event pairs around each launch
   struct ProfRec { cudaEvent_t a, b; int cls; double flops; double bytes; };

@@ -18,6 +18,8 @@
 // Rows are grouped (grp_in rows per batch item, of which grp_valid are real) so that the one
 // row per item that straddles the next item's left padding is computed but never stored.
 #pragma once
+#include <type_traits>
+
 #include "ptx_sm100.cuh"
 
 namespace mc {
@@ -42,6 +44,7 @@ struct GemmParams {
   int rope_cols;    // RoPE applies to output columns [0, rope_cols), 64-wide heads
   int rope_period;  // position = rope_offset + (row within group) % rope_period
   int rope_offset;
+  int one = 1;      // always 1; opaque to the compiler (see gemm_epilogue_slab_fast)
 };
 
 constexpr int GEMM_BM = 128;
@@ -61,11 +64,17 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;  // + alignment slack
 };
 
+// tanh-GELU as 5 FP32 ops + one MUFU.TANH:  u = x * (k0 + k0*k1*x^2),  y = hx + hx*tanh(u), hx = x/2.
+// Every kernel (GEMM epilogues of all variants, the first conv) uses this one function, so an activation
+// computed through different tilings is bit-identical.
 __device__ __forceinline__ float gelu_tanh_f(float x) {
-  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  const float x2 = x * x;
+  const float inner = fmaf(x2, 0.7978845608028654f * 0.044715f, 0.7978845608028654f);
+  const float u = x * inner;
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  return 0.5f * x * (1.0f + t);
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -242,6 +251,201 @@ __device__ __forceinline__ void gemm_epilogue_slab(const GemmParams& p, const CU
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Specialised epilogues for the three GEMMs that carry the transformer (QKV + RoPE, W1 + GELU, Wo / W2
+// residual): same arithmetic as gemm_epilogue_slab, restructured so that the epilogue of a K = 1024 tile
+// fits under its main loop:
+//   * the mode is a template parameter (no dead register ranges: the generic version keeps bias, RoPE
+//     angles and both raw halves live at once and sits at the 255-register cap);
+//   * the tile's 256 bias values are staged once per tile in shared memory (1 KB, shared by the four
+//     epilogue warps, guarded by a 128-thread named barrier) instead of 64 registers refilled from L2
+//     per chunk;
+//   * TMEM loads are software-pipelined: the tcgen05.ld of chunk c+1 is in flight while chunk c is
+//     computed and stored (measured with clock64: a drain-only epilogue spent ~380 cycles per
+//     tcgen05.ld.x32 + wait, none of it overlapped).
+// Requirements (checked by the launcher): TMA-store output, bias present, N a multiple of BN.
+// ---------------------------------------------------------------------------------------------
+enum : int { EPI_GENERIC = 0, EPI_ROPE_BF16 = 1, EPI_GELU_BF16 = 2, EPI_RESID_F32 = 3 };
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// Orders every later use of v[] after the preceding tcgen05.wait::ld (asm volatile statements keep their order;
+// this one "modifies" the registers, so the compiler cannot hoist a consumer above the wait).
+__device__ __forceinline__ void reg_fence32(uint32_t (&v)[32]) {
+  asm volatile(""
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+
+struct EpiFastRegs {
+  float rc[32], rs[32];    // RoPE variant only (dead otherwise)
+  int rope_pos = -1;
+  int buf_sel = 0;
+};
+
+__device__ __forceinline__ float4 lds_f4(const float* smem_ptr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(smem_ptr)));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(void* smem_ptr, uint4 w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(smem_ptr)), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_fast_chunk(const GemmParams& p, const CUtensorMap* map_out_p, uint32_t (&lo)[32],
+                                               uint32_t (&hi)[32], const float* sb /*this chunk's 64 biases (smem)*/,
+                                               int n0, int row0, int lane, uint8_t* my_bufs, EpiFastRegs& st) {
+  float v[64];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    v[j] = __uint_as_float(lo[j]);
+    v[32 + j] = __uint_as_float(hi[j]);
+  }
+  // `p.one` is always 1, but the compiler cannot know: the branch puts the arithmetic in its own basic block, so
+  // ptxas cannot hoist it above the tcgen05.ld of the NEXT chunk that the caller has just issued (without it the
+  // load was sunk below all 64 activations and its latency overlapped only the 8 shared-memory stores).
+  if (p.one != 0) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b0 = lds_f4(sb + j);
+      const float4 b1 = lds_f4(sb + 32 + j);
+      v[j] += b0.x; v[j + 1] += b0.y; v[j + 2] += b0.z; v[j + 3] += b0.w;
+      v[32 + j] += b1.x; v[32 + j + 1] += b1.y; v[32 + j + 2] += b1.z; v[32 + j + 3] += b1.w;
+    }
+    if (EPI == EPI_GELU_BF16) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) v[j] = gelu_tanh_f(v[j]);
+    }
+    if (EPI == EPI_ROPE_BF16) {
+      if (n0 < p.rope_cols) {   // warp-uniform: q and k heads rotate, v heads do not
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x1 = v[j], x2 = v[32 + j];
+          v[j] = x1 * st.rc[j] - x2 * st.rs[j];
+          v[32 + j] = x1 * st.rs[j] + x2 * st.rc[j];
+        }
+      }
+    }
+  }
+  const int sw = lane & 7;
+  if (EPI == EPI_RESID_F32) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint8_t* buf = my_bufs + st.buf_sel * kEpiBufBytes;
+      if (lane == 0) tma_wait_group_read<1>();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float* vv = v + 32 * half + 4 * j;
+        sts_u4(buf + lane * 128 + ((j ^ sw) << 4), make_uint4(__float_as_uint(vv[0]), __float_as_uint(vv[1]), __float_as_uint(vv[2]),
+                                                               __float_as_uint(vv[3])));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_2d(map_out_p, buf, n0 + 32 * half, row0);
+        tma_commit_group();
+      }
+      st.buf_sel ^= 1;
+    }
+  } else {
+    uint8_t* buf = my_bufs + st.buf_sel * kEpiBufBytes;
+    if (lane == 0) tma_wait_group_read<1>();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint4 w;
+      w.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+      w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+      w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+      w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+      sts_u4(buf + lane * 128 + ((j ^ sw) << 4), w);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(map_out_p, buf, n0, row0);
+      tma_commit_group();
+    }
+    st.buf_sel ^= 1;
+  }
+}
+
+template <int BN, int EPI>
+__device__ __forceinline__ void gemm_epilogue_slab_fast(const GemmParams& p, const CUtensorMap* map_out_p, uint32_t tmem_acc,
+                                                        int row_base, int n_base, int q, int lane, uint8_t* my_bufs,
+                                                        float* sbias /*[BN] shared by the 4 epilogue warps*/, EpiFastRegs& st,
+                                                        uint64_t* ready_bar, uint32_t ready_parity) {
+  static_assert(BN % 128 == 0, "fast epilogue: chunk pairs");
+  // stage the tile's bias: all four warps are past their reads of the previous tile's values, then each writes a quarter
+  named_bar_sync(1, 128);
+  {
+    const int i = q * 32 + lane;                      // 128 threads x 2 floats (BN = 256) or 1 float (BN = 128)
+#pragma unroll
+    for (int u = 0; u < BN / 128; ++u) {
+      const float bv = __ldg(p.bias + n_base + i * (BN / 128) + u);
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(sbias + i * (BN / 128) + u)), "f"(bv) : "memory");
+    }
+  }
+  if (EPI == EPI_ROPE_BF16) {
+    if (n_base < p.rope_cols) {
+      const int g = row_base + q * 32 + lane;
+      const int r = g % p.grp_in;                     // grp_in = INT_MAX for plain GEMMs: r = g
+      const int pos = p.rope_offset + r % p.rope_period;
+      if (pos != st.rope_pos) {
+        st.rope_pos = pos;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          st.rc[j] = __ldg(p.rope_cos + static_cast<long long>(j) * p.rope_ld + pos);
+          st.rs[j] = __ldg(p.rope_sin + static_cast<long long>(j) * p.rope_ld + pos);
+        }
+      }
+    }
+  }
+  named_bar_sync(1, 128);
+  mbar_wait(ready_bar, ready_parity);  // accumulator complete
+  tc_fence_after();
+
+  const int row0 = row_base + q * 32;
+  const uint32_t tbase = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+  uint32_t a_lo[32], a_hi[32], b_lo[32], b_hi[32];
+  tmem_ld_32x32b_x32(tbase, a_lo);
+  tmem_ld_32x32b_x32(tbase + 32, a_hi);
+  tmem_ld_wait();
+  reg_fence32(a_lo);
+  reg_fence32(a_hi);
+#pragma unroll
+  for (int c = 0; c < BN / 64; c += 2) {
+    // chunk c from the A registers while chunk c+1 streams into B
+    tmem_ld_32x32b_x32(tbase + (c + 1) * 64, b_lo);
+    tmem_ld_32x32b_x32(tbase + (c + 1) * 64 + 32, b_hi);
+    reg_fence32(a_lo);   // pins the math on chunk c BEHIND the loads just issued (the compiler would otherwise
+    reg_fence32(a_hi);   // hoist it above them, and the tcgen05.ld latency would be exposed again)
+    epi_fast_chunk<EPI>(p, map_out_p, a_lo, a_hi, sbias + c * 64, n_base + c * 64, row0, lane, my_bufs, st);
+    tmem_ld_wait();
+    reg_fence32(b_lo);
+    reg_fence32(b_hi);
+    if (c + 2 < BN / 64) {
+      tmem_ld_32x32b_x32(tbase + (c + 2) * 64, a_lo);
+      tmem_ld_32x32b_x32(tbase + (c + 2) * 64 + 32, a_hi);
+    }
+    reg_fence32(b_lo);
+    reg_fence32(b_hi);
+    epi_fast_chunk<EPI>(p, map_out_p, b_lo, b_hi, sbias + (c + 1) * 64, n_base + (c + 1) * 64, row0, lane, my_bufs, st);
+    if (c + 2 < BN / 64) {
+      tmem_ld_wait();
+      reg_fence32(a_lo);
+      reg_fence32(a_hi);
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -390,10 +594,12 @@ struct Gemm2Cfg {
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kEpiBytes = 4 * 2 * kEpiBufBytes;
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
+  static constexpr int kBiasBytes = BN * 4;   // per-tile bias staging of the specialised epilogues
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + kBiasBytes + 1024;
+  static_assert(kSmemBytes <= 232448, "CTA-pair GEMM exceeds 227 KB of shared memory");
 };
 
-template <int BN>
+template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                         const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
@@ -407,6 +613,7 @@ gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* sbias = reinterpret_cast<float*>(bar_base + Cfg::kBarBytes);   // [BN], fast epilogues only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -495,14 +702,19 @@ gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   } else if (warp < 4) {
     const int q = warp;
     uint8_t* my_bufs = epi_base + q * 2 * kEpiBufBytes;
-    EpiRegs st;
+    typename std::conditional<EPI == EPI_GENERIC, EpiRegs, EpiFastRegs>::type st;
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      gemm_epilogue_slab<BN>(p, &map_out, tmem_base + acc * BN, m_blk * 2 * GEMM_BM + rank * GEMM_BM, n_blk * BN, q, lane,
-                             my_bufs, st, &tmem_full[acc], acc_phase);
+      if constexpr (EPI == EPI_GENERIC) {
+        gemm_epilogue_slab<BN>(p, &map_out, tmem_base + acc * BN, m_blk * 2 * GEMM_BM + rank * GEMM_BM, n_blk * BN, q, lane,
+                               my_bufs, st, &tmem_full[acc], acc_phase);
+      } else {
+        gemm_epilogue_slab_fast<BN, EPI>(p, &map_out, tmem_base + acc * BN, m_blk * 2 * GEMM_BM + rank * GEMM_BM, n_blk * BN, q,
+                                         lane, my_bufs, sbias, st, &tmem_full[acc], acc_phase);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));

@@ -62,6 +62,39 @@ def test_gemm_cta_pair_kernel(gen, M, N, K, mode):
     assert err < tol, f"max abs err {err}"
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (300, 512, 128), (1000, 3072, 512), (2560, 512, 2048), (25600, 1024, 1024)])
+@pytest.mark.parametrize("mode", ["rope", "gelu", "residual"])
+def test_specialised_pair_epilogues_are_bit_identical_to_generic(gen, M, N, K, mode):
+    """The mode-specialised, software-pipelined epilogues of the CTA-pair GEMM reorder loads, not arithmetic."""
+    A = _rand((M, K), seed=31).to(torch.bfloat16)
+    W = (_rand((N, K), seed=32) / math.sqrt(K)).to(torch.bfloat16)
+    bias = _rand((N,), seed=33)
+    x0 = _rand((M, N), seed=34)
+
+    def run():
+        if mode == "rope":
+            return gen.op_gemm(A, W, bias=bias, out_mode=0, rope_cols=(N // 128) * 64, rope_period=100, block_n=512)
+        if mode == "gelu":
+            return gen.op_gemm(A, W, bias=bias, act=1, out_mode=0, block_n=512)
+        out = x0.clone()
+        gen.op_gemm(A, W, bias=bias, out_mode=2, out=out, block_n=512)
+        return out
+
+    try:
+        gen.set_option("fast_epilogue", 1)
+        fast = run()
+        gen.set_option("fast_epilogue", 0)
+        generic = run()
+    finally:
+        gen.set_option("fast_epilogue", 1)
+    assert torch.equal(fast, generic)
+    ref = A.float() @ W.float().t() + bias
+    if mode == "gelu":
+        assert (fast.float() - gelu_tanh(ref)).abs().max().item() < 0.03
+    elif mode == "residual":
+        assert (fast - (x0 + ref)).abs().max().item() < 2e-3
+
+
 @pytest.mark.parametrize("act", [0, 1])
 def test_gemm_bf16_out_bias_act(gen, act):
     M, N, K = 515, 1024, 512

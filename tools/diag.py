@@ -181,5 +181,43 @@ def diag_e2e():
     g.smoke()
 
 
+def diag_block_gemms():
+    """The four GEMMs of one transformer block at M = 25 600 and 102 400: specialised (pipelined) epilogue vs the
+    generic one vs cuBLAS (plain GEMM, no epilogue), 20 back-to-back launches each."""
+    gen = make_gen(pkg.DEFAULT_SPEC)
+    torch.manual_seed(0)
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 20
+
+    for M in (25600, 102400):
+        for (name, N, K, kw) in [("QKV + bias + RoPE", 3072, 1024, dict(out_mode=0, rope_cols=2048, rope_period=100)),
+                                 ("Wo  + bias, fp32 residual", 1024, 1024, dict(out_mode=2)),
+                                 ("W1  + bias + GELU", 4096, 1024, dict(out_mode=0, act=1)),
+                                 ("W2  + bias, fp32 residual", 1024, 4096, dict(out_mode=2))]:
+            A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+            W = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
+            bias = torch.randn(N, device="cuda")
+            out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16 if kw["out_mode"] == 0 else torch.float32)
+            fl = 2.0 * M * N * K
+            res = {}
+            for tag, fast in (("specialised", 1), ("generic", 0)):
+                gen.set_option("fast_epilogue", fast)
+                ms = timeit(lambda: gen.op_gemm(A, W, bias=bias, out=out, **kw))
+                res[tag] = ms
+            gen.set_option("fast_epilogue", 1)
+            ref = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+            res["cuBLAS (no epilogue)"] = timeit(lambda: torch.matmul(A, W.t(), out=ref))
+            print(f"M{M} {name:28s} " + "  ".join(f"{k}: {v * 1e3:7.1f} us {fl / v / 1e9:6.0f} TF/s" for k, v in res.items()))
+
+
 if __name__ == "__main__":
-    {"gemm": diag_gemm, "attn": diag_attn, "vq": diag_vq, "e2e": diag_e2e, "epi": diag_epi, "cyc": diag_epi_cycles}[sys.argv[1]]()
+    {"block": diag_block_gemms, "gemm": diag_gemm, "attn": diag_attn, "vq": diag_vq, "e2e": diag_e2e, "epi": diag_epi, "cyc": diag_epi_cycles}[sys.argv[1]]()
