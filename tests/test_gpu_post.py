@@ -28,7 +28,7 @@ def g(golden_dir):
 
 @pytest.fixture(scope="module")
 def gen():
-    return pkg.B200Generator(pkg.TINY_SPEC, pkg.init_random_weights(pkg.TINY_SPEC, seed=0), device="cuda", max_positions=256)
+    return pkg.B200Generator(pkg.TINY_SPEC, pkg.init_random_weights(pkg.TINY_SPEC, seed=0), device="cuda", max_positions=1024)
 
 
 @pytest.mark.parametrize("tag,target", [("plain", 0.0), ("rms", 0.05)])
