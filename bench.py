@@ -170,6 +170,11 @@ def main():
         return
 
     import torch.distributed as dist
+    # Anything a library prints while the job runs (NCCL's version banner goes to stdout) must not land in front of
+    # the ONE JSON line: fd 1 points at stderr until the line is printed.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -302,7 +307,10 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(args.cpu_sample_secs, 1, 1, cores)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

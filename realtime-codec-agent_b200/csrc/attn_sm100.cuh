@@ -514,10 +514,12 @@ attention_window_sm100_v3_kernel(const __grid_constant__ CUtensorMap map_q, cons
   for (int i = threadIdx.x; i < 2 * Cfg::kPBytes / 16; i += ATT2_THREADS)
     reinterpret_cast<uint4*>(p_base)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
 
   if (warp == 8) {
     if (lane == 0) {
@@ -717,8 +719,8 @@ inline int launch_attention_sm100_v3_nkv(mc_handle* h, const bf16* qkv, bf16* ou
   const long long items = (long long)B * s.n_heads * (q_tiles - (F - out_rows) / ATT_BQ);
   if (items > INT_MAX) return h->fail(MC_ERR_ARG, "attention: too many tiles");
   const int grid = (int)std::min<long long>(items, h->num_sms);
-  attention_window_sm100_v3_kernel<NKV><<<grid, ATT2_THREADS, Cfg::kSmemBytes, stream>>>(
-      *mq, *mkv, out, B, F, s.n_heads, s.window_left, out_rows, 0.125f * 1.4426950408889634f);
+  mc_launch(h, attention_window_sm100_v3_kernel<NKV>, dim3(grid), dim3(ATT2_THREADS), Cfg::kSmemBytes, stream, *mq, *mkv, out, B, F,
+            s.n_heads, s.window_left, out_rows, 0.125f * 1.4426950408889634f);
   MC_LAUNCH_CHECK(h, "attention_window_sm100_v3_kernel");
   return MC_OK;
 }

@@ -173,6 +173,8 @@ vq_simt_kernel(const float* __restrict__ z, int Mq, int F, int keep, const float
 // ranges, so scanning them in order with a strict '<' keeps the lowest index on ties.
 __global__ void vq_merge_kernel(const VqPartial* __restrict__ partial, int Mq, int splits,
                                 long long* __restrict__ codes, float* __restrict__ margin) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= Mq) return;
   float best = INFINITY, second = INFINITY;

@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(256)
 conv_first_kernel(const float* __restrict__ wav, long long ld, int T, int B, int T0, int s0, int C0,
                   const float* __restrict__ w /*[KT, C0]*/, const float* __restrict__ bias,
                   __nv_bfloat16* __restrict__ out, int pad_rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   // A thread keeps ONE group of 8 output channels for its whole life: its KT x 8 weights and 8 biases
   // live in registers, so the inner loop has no shared-memory traffic at all.
   const int cgroups = C0 / 8;
@@ -68,6 +70,8 @@ conv_first_kernel(const float* __restrict__ wav, long long ld, int T, int B, int
 __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                __nv_bfloat16* __restrict__ out, int M, int d, float eps, int grp_in,
                                long long grp_stride, long long grp_off) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
@@ -103,6 +107,8 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 rmsnorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ out, int M,
                     float eps, int grp_in, long long grp_stride, long long grp_off) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int d = NV * 128;
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -138,6 +144,8 @@ rmsnorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma
 // ---------------------------------------------------------------------------------------------
 __global__ void compact_rows_kernel(const float4* __restrict__ x, float4* __restrict__ y, int B, int r_in, int r_out,
                                     int d4) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(B) * r_out * d4;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -155,6 +163,8 @@ __global__ void compact_rows_kernel(const float4* __restrict__ x, float4* __rest
 // ---------------------------------------------------------------------------------------------
 __global__ void gather_stem_kernel(const float4* __restrict__ stem, float4* __restrict__ x, int B, int F, int pre,
                                    int fstep, int d4) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int per = F - pre;
   const long long total = static_cast<long long>(B) * per * d4;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -173,6 +183,8 @@ __global__ void gather_stem_kernel(const float4* __restrict__ stem, float4* __re
 // ---------------------------------------------------------------------------------------------
 __global__ void embed_codes_kernel(const long long* __restrict__ codes, const float* __restrict__ table /*[K,16]*/,
                                    int K, __nv_bfloat16* __restrict__ out, long long M) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = M * 8;  // 8 x 16-byte pieces per 64-wide row
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -224,6 +236,8 @@ template <int MAXS>
 __global__ void tconv_last_kernel(const __nv_bfloat16* __restrict__ x, int B, int Tin, int Cin, int s,
                                   const float* __restrict__ w /*[Cin, 2*s]*/, const float* __restrict__ bias,
                                   float* __restrict__ out, int keep) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sw[];  // [Cin * 2*s]
   for (int i = threadIdx.x; i < Cin * 2 * s; i += blockDim.x) sw[i] = w[i];
   __syncthreads();

@@ -57,7 +57,7 @@ int launch_gemm_bn(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   const double valid_rows = c.grp_in == INT_MAX ? (double)c.M : (double)c.M / c.grp_in * c.grp_valid;
   const double out_bytes = valid_rows * c.N * (c.out_mode == OUT_BF16 ? 2.0 : (c.out_mode == OUT_F32 ? 4.0 : 8.0));
   McProfScope prof(h, 0, 2.0 * valid_rows * c.N * c.K, valid_rows * c.a_k_wrap * 2.0 + (double)c.N * c.K * 2.0 + out_bytes, stream);
-  gemm_bf16_sm100_kernel<BN><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, stream>>>(*ma, *mb, *mo, p);
+  mc_launch(h, gemm_bf16_sm100_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), GemmCfg<BN>::kSmemBytes, stream, *ma, *mb, *mo, p);
   MC_LAUNCH_CHECK(h, "gemm_bf16_sm100_kernel");
   return MC_OK;
 }
@@ -73,7 +73,7 @@ int launch_gemm_pair_epi(mc_handle* h, const GemmCall& c, const GemmParams& p, c
                                     Gemm2Cfg<BN>::kSmemBytes));
     attr_set = true;
   }
-  gemm2_bf16_sm100_kernel<BN, EPI><<<2 * pairs, GEMM_THREADS, Gemm2Cfg<BN>::kSmemBytes, stream>>>(*ma, *mb, *mo, p);
+  mc_launch(h, gemm2_bf16_sm100_kernel<BN, EPI>, dim3(2 * pairs), dim3(GEMM_THREADS), Gemm2Cfg<BN>::kSmemBytes, stream, *ma, *mb, *mo, p);
   MC_LAUNCH_CHECK(h, "gemm2_bf16_sm100_kernel");
   return MC_OK;
 }
@@ -157,11 +157,11 @@ int launch_rmsnorm(mc_handle* h, const float* x, const float* gamma, bf16* out, 
   McProfScope prof(h, 3, 0.0, (double)M * d * 6.0, stream);
   const float eps = h->spec.norm_eps;
   switch (d % 128 == 0 ? d / 128 : 0) {   // register-resident rows (x read once) for the widths in use
-    case 1: rmsnorm_rows_kernel<1><<<grid, warps * 32, 0, stream>>>(x, gamma, out, M, eps, grp_in, grp_stride, grp_off); break;
-    case 2: rmsnorm_rows_kernel<2><<<grid, warps * 32, 0, stream>>>(x, gamma, out, M, eps, grp_in, grp_stride, grp_off); break;
-    case 4: rmsnorm_rows_kernel<4><<<grid, warps * 32, 0, stream>>>(x, gamma, out, M, eps, grp_in, grp_stride, grp_off); break;
-    case 8: rmsnorm_rows_kernel<8><<<grid, warps * 32, 0, stream>>>(x, gamma, out, M, eps, grp_in, grp_stride, grp_off); break;
-    default: rmsnorm_kernel<<<grid, warps * 32, 0, stream>>>(x, gamma, out, M, d, eps, grp_in, grp_stride, grp_off);
+    case 1: mc_launch(h, rmsnorm_rows_kernel<1>, dim3(grid), dim3(warps * 32), 0, stream, x, gamma, out, M, eps, grp_in, (long long)grp_stride, (long long)grp_off); break;
+    case 2: mc_launch(h, rmsnorm_rows_kernel<2>, dim3(grid), dim3(warps * 32), 0, stream, x, gamma, out, M, eps, grp_in, (long long)grp_stride, (long long)grp_off); break;
+    case 4: mc_launch(h, rmsnorm_rows_kernel<4>, dim3(grid), dim3(warps * 32), 0, stream, x, gamma, out, M, eps, grp_in, (long long)grp_stride, (long long)grp_off); break;
+    case 8: mc_launch(h, rmsnorm_rows_kernel<8>, dim3(grid), dim3(warps * 32), 0, stream, x, gamma, out, M, eps, grp_in, (long long)grp_stride, (long long)grp_off); break;
+    default: mc_launch(h, rmsnorm_kernel, dim3(grid), dim3(warps * 32), 0, stream, x, gamma, out, M, d, eps, grp_in, (long long)grp_stride, (long long)grp_off);
   }
   MC_LAUNCH_CHECK(h, "rmsnorm_kernel");
   return MC_OK;
@@ -250,8 +250,8 @@ int run_layers(mc_handle* h, const char* prefix, int n_layers, const StackBufs& 
     if (Ro < Ri) {
       const long long items = (long long)Mo * (d / 4);
       McProfScope prof(h, 3, 0.0, (double)Mo * d * 8.0, stream);
-      compact_rows_kernel<<<ew_grid(h, items, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(x),
-                                                                    reinterpret_cast<float4*>(xalt), B, Ri, Ro, d / 4);
+      mc_launch(h, compact_rows_kernel, dim3(ew_grid(h, items, 256)), dim3(256), 0, stream, reinterpret_cast<const float4*>(x),
+                reinterpret_cast<float4*>(xalt), B, Ri, Ro, d / 4);
       MC_LAUNCH_CHECK(h, "compact_rows_kernel");
       std::swap(x, xalt);
       rows = Ro;
@@ -273,8 +273,8 @@ int run_layers(mc_handle* h, const char* prefix, int n_layers, const StackBufs& 
   if (rows > keep_rows) {  // no layers (or window_left = 0 corner cases): compact at the end
     const int Ro = keep_rows;
     const long long items = (long long)B * Ro * (d / 4);
-    compact_rows_kernel<<<ew_grid(h, items, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(x),
-                                                                  reinterpret_cast<float4*>(xalt), B, rows, Ro, d / 4);
+    mc_launch(h, compact_rows_kernel, dim3(ew_grid(h, items, 256)), dim3(256), 0, stream, reinterpret_cast<const float4*>(x),
+              reinterpret_cast<float4*>(xalt), B, rows, Ro, d / 4);
     MC_LAUNCH_CHECK(h, "compact_rows_kernel");
     std::swap(x, xalt);
   }
@@ -344,11 +344,11 @@ int run_conv_stack(mc_handle* h, const ConvPlan& cp, uint8_t* base, const float*
     McProfScope prof(h, 3, 2.0 * B * Tl[0] * 2 * s0 * C0, (double)B * Tvalid * 4.0 + (double)B * Tl[0] * C0 * 2.0, stream);
     bf16* o0 = reinterpret_cast<bf16*>(base + cp.off[0]);
     if (2 * s0 == 8)
-      conv_first_kernel<8><<<grid, threads, 0, stream>>>(wav, ld, Tvalid, B, Tl[0], s0, C0, h->ptr<float>("enc.conv0.w"),
-                                                          h->ptr<float>("enc.conv0.b"), o0, s.conv_strides[1]);
+      mc_launch(h, conv_first_kernel<8>, dim3(grid), dim3(threads), 0, stream, wav, (long long)ld, Tvalid, B, Tl[0], s0, C0,
+                h->ptr<float>("enc.conv0.w"), h->ptr<float>("enc.conv0.b"), o0, (int)s.conv_strides[1]);
     else
-      conv_first_kernel<16><<<grid, threads, 0, stream>>>(wav, ld, Tvalid, B, Tl[0], s0, C0, h->ptr<float>("enc.conv0.w"),
-                                                           h->ptr<float>("enc.conv0.b"), o0, s.conv_strides[1]);
+      mc_launch(h, conv_first_kernel<16>, dim3(grid), dim3(threads), 0, stream, wav, (long long)ld, Tvalid, B, Tl[0], s0, C0,
+                h->ptr<float>("enc.conv0.w"), h->ptr<float>("enc.conv0.b"), o0, (int)s.conv_strides[1]);
     MC_LAUNCH_CHECK(h, "conv_first_kernel");
   }
   for (int i = 1; i < n; ++i) {
@@ -444,9 +444,8 @@ int encode_impl(mc_handle* h, const float* wav, int64_t ld, int B, int T, int ke
     MC_TRY(run_conv_stack(h, cp_pre, base, wav, ld, pre * hop, sb.x, (int64_t)F * d, stream));
     const long long items = (long long)B * (F - pre) * (d / 4);
     McProfScope prof(h, 3, 0.0, (double)B * (F - pre) * d * 8.0, stream);
-    gather_stem_kernel<<<ew_grid(h, items, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(stem),
-                                                                 reinterpret_cast<float4*>(sb.x), B, F, pre,
-                                                                 (int)(ld / hop), d / 4);
+    mc_launch(h, gather_stem_kernel, dim3(ew_grid(h, items, 256)), dim3(256), 0, stream, reinterpret_cast<const float4*>(stem),
+              reinterpret_cast<float4*>(sb.x), B, F, pre, (int)(ld / hop), d / 4);
     MC_LAUNCH_CHECK(h, "gather_stem_kernel");
   } else {
     MC_TRY(run_conv_stack(h, cp_full, base, wav, ld, T, sb.x, (int64_t)F * d, stream));
@@ -508,8 +507,8 @@ int decode_impl(mc_handle* h, const int64_t* codes, const float* z_q, int B, int
 
   const int threads = 256;
   if (codes) {
-    embed_codes_kernel<<<ew_grid(h, (long long)M * 8, threads), threads, 0, stream>>>(
-        reinterpret_cast<const long long*>(codes), h->ptr<float>("vq.codebook"), s.codebook_size, a0, M);
+    mc_launch(h, embed_codes_kernel, dim3(ew_grid(h, (long long)M * 8, threads)), dim3(threads), 0, stream,
+              reinterpret_cast<const long long*>(codes), h->ptr<float>("vq.codebook"), (int)s.codebook_size, a0, (long long)M);
     MC_LAUNCH_CHECK(h, "embed_codes_kernel");
   } else {
     pack_latents_kernel<<<ew_grid(h, (long long)M * 8, threads), threads, 0, stream>>>(z_q, a0, M);
@@ -546,9 +545,9 @@ int decode_impl(mc_handle* h, const int64_t* codes, const float* z_q, int B, int
     const long long items = (long long)B * Tin[i];
     const size_t smem = (size_t)dch[i] * 2 * ds[i] * 4;
     McProfScope prof(h, 3, 4.0 * B * Tin[i] * dch[i] * ds[i], (double)B * Tin[i] * dch[i] * 2.0 + (double)B * keep * 4.0, stream);
-    tconv_last_kernel<8><<<ew_grid(h, items, threads), threads, smem, stream>>>(
-        reinterpret_cast<const bf16*>(base + tb_off[i]), B, Tin[i], dch[i], ds[i],
-        h->ptr<float>("dec.up" + std::to_string(i) + ".w"), h->ptr<float>("dec.up" + std::to_string(i) + ".b"), wav, keep);
+    mc_launch(h, tconv_last_kernel<8>, dim3(ew_grid(h, items, threads)), dim3(threads), smem, stream,
+              reinterpret_cast<const bf16*>(base + tb_off[i]), B, Tin[i], dch[i], ds[i],
+              h->ptr<float>("dec.up" + std::to_string(i) + ".w"), h->ptr<float>("dec.up" + std::to_string(i) + ".b"), wav, keep);
     MC_LAUNCH_CHECK(h, "tconv_last_kernel");
   }
   return MC_OK;
@@ -767,6 +766,7 @@ int mc_set_option(mc_handle* h, const char* key, int32_t value) {
   if (k == "shared_stem") h->shared_stem = value != 0;
   else if (k == "gemm_pair") h->gemm_pair = value != 0;
   else if (k == "fast_epilogue") h->fast_epilogue = value != 0;
+  else if (k == "pdl") h->pdl = value != 0;
   else return h->fail(MC_ERR_ARG, "mc_set_option: unknown option '%s'", key);
   return MC_OK;
 }
@@ -1061,9 +1061,9 @@ static int stream_push_codes_impl(mc_stream* s, const int64_t* codes, int32_t n,
                                  cudaMemcpyDeviceToDevice, stream));
     MC_TRY(decode_impl(h, s->dev_codes_out, nullptr, C, new_len, keep, s->dev_wav_out, stream));
     if (emit) {
-      emit_chunk_kernel<<<1, POST_THREADS, 0, stream>>>(s->dev_wav_out, keep, s->emit_chunk, s->emit_fade, has_prev,
-                                                        s->emit_target_rms, s->emit_silence_thr, s->emit_fade_in,
-                                                        s->emit_prev_tail, s->emit_out);
+      mc_launch(h, emit_chunk_kernel, dim3(1), dim3(POST_THREADS), 0, stream, (const float*)s->dev_wav_out, keep, s->emit_chunk,
+                s->emit_fade, has_prev, s->emit_target_rms, s->emit_silence_thr, (const float*)s->emit_fade_in, s->emit_prev_tail,
+                s->emit_out);
       MC_LAUNCH_CHECK(h, "emit_chunk_kernel");
       MC_CUDA(h, cudaMemcpyAsync(s->pin_emit, s->emit_out, (size_t)emit_floats * 4, cudaMemcpyDeviceToHost, stream));
     } else {

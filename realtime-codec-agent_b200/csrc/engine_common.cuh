@@ -13,6 +13,7 @@
 #include <string>
 #include <tuple>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "../../include/magicodec_b200.h"
@@ -60,6 +61,7 @@ struct mc_handle {
   int attn_impl = 0, vq_impl = 0;
   int gemm_pair = 1;  // use the cta_group::2 GEMM where the shape allows
   bool fast_epilogue = true;  // mode-specialised, software-pipelined epilogues in the CTA-pair GEMM
+  bool pdl = true;            // programmatic dependent launch between consecutive kernels of a pass
   bool shared_stem = true;  // overlapping hop-aligned windows share one pass of the conv stack (exact)
   // optional per-class device timing (bench.py's roofline): event pairs around each launch
   struct ProfRec { cudaEvent_t a, b; int cls; double flops; double bytes; };
@@ -122,6 +124,20 @@ struct McProfScope {
     h->prof.push_back(rec);
   }
 };
+
+// Kernel launch with (optionally) the programmatic-stream-serialization attribute; the kernels call pdl_wait()
+// before touching anything a predecessor may have written.
+template <typename... P, typename... A>
+inline void mc_launch(mc_handle* h, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = h->pdl ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);   // errors surface through MC_LAUNCH_CHECK
+}
 
 #define MC_LAUNCH_CHECK(h, what)                                                                  \
   do {                                                                                            \

@@ -488,10 +488,12 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     tmem_alloc(tmem_ptr, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();   // everything above overlapped the previous kernel's tail; nothing below runs before it has finished
 
   if (warp == 4) {
     // ------------------------------------------------------------ TMA producer
@@ -644,11 +646,13 @@ gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     tmem_alloc_pair(tmem_ptr, Cfg::kTmemCols);
     tmem_relinquish_pair();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
 
   if (warp == 4) {
     if (lane == 0) {

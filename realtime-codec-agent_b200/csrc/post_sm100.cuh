@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(POST_THREADS)
 emit_chunk_kernel(const float* __restrict__ wav, int n_have, int chunk, int L, int has_prev, float target_rms,
                   float silence_thr, const float* __restrict__ fade_in, float* __restrict__ prev_tail,
                   float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double scratch[POST_THREADS / 32 + 1];
   const int want = has_prev ? chunk + L : chunk;       // pad_or_trim target (right pad with zeros / trim)
   const int n = min(n_have, want);

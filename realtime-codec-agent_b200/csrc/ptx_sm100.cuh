@@ -27,6 +27,14 @@ __device__ __forceinline__ uint32_t elect_one() {
   return pred;
 }
 
+// ------------------------------------------------- programmatic dependent launch
+// Kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while their predecessor in the
+// stream is still running: pdl_launch_dependents() lets the NEXT kernel be scheduled early, pdl_wait() blocks until
+// the PREVIOUS kernel has completed and its writes are visible.  Everything before pdl_wait() (barrier init, TMEM
+// allocation, descriptor prefetch) overlaps the predecessor's tail.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

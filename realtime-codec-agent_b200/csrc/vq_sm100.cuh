@@ -66,6 +66,8 @@ vq_argmin_sm100_kernel(const __grid_constant__ CUtensorMap map_b, const float* _
     tmem_alloc(tmem_ptr, VQ_TMEM_COLS);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
+  pdl_wait();   // the queries below are the previous kernel's output
   // ---- build the A tile (split-bf16 queries) directly in the swizzled K-major layout
   if (threadIdx.x < 128) {
     const int r = threadIdx.x;
@@ -206,11 +208,11 @@ inline int launch_vq_sm100(mc_handle* h, const float* z, int n_items, int F, int
     MC_CUDA(h, cudaFuncSetAttribute(vq_argmin_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VQ_SMEM_BYTES));
     attr_set = true;
   }
-  vq_argmin_sm100_kernel<<<dim3(row_tiles, splits), VQ_THREADS, VQ_SMEM_BYTES, stream>>>(
-      *mb, z, Mq, F, keep, tiles_total, splits, reinterpret_cast<VqPartial*>(scratch));
+  mc_launch(h, vq_argmin_sm100_kernel, dim3(row_tiles, splits), dim3(VQ_THREADS), VQ_SMEM_BYTES, stream, *mb, z, Mq, F, keep,
+            tiles_total, splits, reinterpret_cast<VqPartial*>(scratch));
   MC_LAUNCH_CHECK(h, "vq_argmin_sm100_kernel");
-  vq_merge_kernel<<<(Mq + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const VqPartial*>(scratch), Mq, splits,
-                                                        reinterpret_cast<long long*>(codes), margin);
+  mc_launch(h, vq_merge_kernel, dim3((Mq + 255) / 256), dim3(256), 0, stream, reinterpret_cast<const VqPartial*>(scratch), Mq,
+            splits, reinterpret_cast<long long*>(codes), margin);
   MC_LAUNCH_CHECK(h, "vq_merge_kernel");
   return MC_OK;
 }

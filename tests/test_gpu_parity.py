@@ -145,6 +145,26 @@ def test_shared_conv_stem_is_exact(bundle, ld, T, B):
     assert torch.equal(gen.encode(mat), c0)
 
 
+def test_programmatic_dependent_launch_changes_nothing(bundle):
+    """Kernels of a pass are chained with programmatic dependent launch (prologues overlap the predecessor's tail,
+    griddepcontrol.wait before the first dependent access): results must equal fully serialised launches."""
+    name, spec, w, g, gen = bundle
+    wav = torch.from_numpy(g["wav0"]).cuda()
+    outs = []
+    try:
+        for pdl in (1, 0, 1):
+            gen.set_option("pdl", pdl)
+            c, m, z = gen.encode(wav, row_stride=1600, num_windows=5, window_samples=32000, return_margin=True, return_latents=True)
+            rec = gen.decode(c[:2], keep_last_samples=1920)
+            one = gen.encode(wav[None, :32000], keep_last_frames=1)
+            outs.append((c, m, z, rec, one))
+    finally:
+        gen.set_option("pdl", 1)
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert torch.equal(a, b)
+
+
 def test_unaligned_window_stride_falls_back(bundle):
     name, spec, w, g, gen = bundle
     wav = torch.from_numpy(g["wav0"]).cuda()
