@@ -64,12 +64,19 @@ def plan_stream(n_samples: int, chunk_samples: int, context_samples: int, sample
 
 
 def encode_streams(gen, streams: Sequence[torch.Tensor], chunk_secs: float = 0.1, context_secs: float = 2.0,
-                   batch_size: int = 256, fuse_batches: int = 1) -> List[torch.Tensor]:
+                   batch_size: int = 256, fuse_batches: int = 1, causal_warmup: bool = True) -> List[torch.Tensor]:
     """Encode mono streams (1-D fp32 device tensors) -> one int64 code tensor per stream.
 
     ``batch_size`` is the reference CLI's windows-per-forward flag.  Per-window results do not depend on
     how windows are grouped into launches (tested bit-exact), so ``fuse_batches`` consecutive batches may
-    be issued as ONE engine call: fewer, larger launches quantise better onto 74 CTA pairs."""
+    be issued as ONE engine call: fewer, larger launches quantise better onto 74 CTA pairs.
+
+    ``causal_warmup``: the warm-up windows of a stream (chunks 0..18 at the default sizes: context shorter than
+    2.0 s) all start at sample 0, so each is a PREFIX of the longest one.  The network is causal end to end
+    (causal convs, causal windowed attention, window-relative RoPE), so frame t of a prefix equals frame t of the
+    longer window: ONE full-frame encode of the longest warm-up window yields every warm-up chunk's codes instead
+    of 19 launches of growing length per stream.  On the engine this is bit-identical (masked keys add exact
+    zeros; tested on the GPU against ``causal_warmup=False``)."""
     batch_size = batch_size * max(1, int(fuse_batches))
     sr, hop = gen.sample_rate, gen.hop
     framerate = sr / hop
@@ -92,11 +99,31 @@ def encode_streams(gen, streams: Sequence[torch.Tensor], chunk_secs: float = 0.1
             codes = gen.encode(view, keep_last_frames=keep, row_stride=chunk, num_windows=nb, window_samples=context)
             pieces[si][first + b0] = codes.reshape(-1)          # consecutive chunks, already in order
 
-    # warm-up / ragged windows: group across streams by (length, keep)
+    # warm-up windows as prefixes of the longest one (see docstring)
+    done: List[set] = [set() for _ in streams]
+    if causal_warmup and chunk % hop == 0:
+        cf = chunk // hop
+        prefix_groups: Dict[int, List[Tuple[int, List[Window]]]] = {}
+        for si, (irr, _) in enumerate(plans):
+            warm = [w for w in irr if w.start == 0 and w.length == (w.chunk + 1) * chunk and w.keep == cf]
+            if len(warm) >= 2:
+                prefix_groups.setdefault(max(w.length for w in warm), []).append((si, warm))
+        for length, items in prefix_groups.items():
+            for b0 in range(0, len(items), batch_size):
+                part = items[b0:b0 + batch_size]
+                batch = torch.stack([streams[si][:length] for si, _ in part])
+                codes = gen.encode(batch, keep_last_frames=0)                      # every frame of the longest prefix
+                for row, (si, warm) in enumerate(part):
+                    for w in warm:
+                        pieces[si][w.chunk] = codes[row, (w.chunk + 1) * cf - w.keep:(w.chunk + 1) * cf]
+                        done[si].add(w.chunk)
+
+    # remaining warm-up / ragged windows: group across streams by (length, keep)
     groups: Dict[Tuple[int, int], List[Tuple[int, Window]]] = {}
     for si, (irr, _) in enumerate(plans):
         for w in irr:
-            groups.setdefault((w.length, w.keep), []).append((si, w))
+            if w.chunk not in done[si]:
+                groups.setdefault((w.length, w.keep), []).append((si, w))
     for (length, keep), items in groups.items():
         for b0 in range(0, len(items), batch_size):
             part = items[b0:b0 + batch_size]

@@ -26,17 +26,30 @@ def test_encode_streams_equals_chunked_tokenize(oracle, n_samples):
     ref = tok.chunked_tokenize_audio(wav.numpy(), 0.1)
     ref_codes = np.array([ord(c) - tok.unicode_offset for c in ref])
     gen = OracleBackedGen(oracle)
-    got = corpus.encode_streams(gen, [wav], 0.1, 2.0, batch_size=8)[0].numpy()
+    got = corpus.encode_streams(gen, [wav], 0.1, 2.0, batch_size=8, causal_warmup=False)[0].numpy()
     assert np.array_equal(got, ref_codes)
+    # warm-up chunks taken from ONE prefix window (causality): on the fp32 CPU oracle a different sequence length may
+    # move last bits, so frames are compared where the oracle's own top-2 margin is clear
+    fast = corpus.encode_streams(OracleBackedGen(oracle), [wav], 0.1, 2.0, batch_size=8)[0].numpy()
+    assert fast.shape == ref_codes.shape
+    with torch.no_grad():
+        _, idx, margin = oracle.quantizer.inference(oracle.encoder(oracle.pad_audio(wav[None, :32000])), return_margin=True)
+    n_warm = min(len(ref_codes), 95)
+    clear = margin[0, :n_warm].numpy() > 1e-3
+    assert np.array_equal(fast[:n_warm][clear], ref_codes[:n_warm][clear]) and clear.mean() > 0.9
+    assert np.array_equal(fast[n_warm:], ref_codes[n_warm:])
 
 
 def test_streams_are_batched_across_files(oracle):
     gen = OracleBackedGen(oracle)
     a, b = pkg.synth_audio(36800, file_id=1), pkg.synth_audio(36800, file_id=2)
-    both = corpus.encode_streams(gen, [a, b], 0.1, 2.0, batch_size=16)
+    both = corpus.encode_streams(gen, [a, b], 0.1, 2.0, batch_size=16, causal_warmup=False)
     assert (2, 1600) in gen.calls and (2, 30400) in gen.calls          # warm-up windows of both files share launches
-    solo = corpus.encode_streams(OracleBackedGen(oracle), [b], 0.1, 2.0, batch_size=16)[0]
+    solo = corpus.encode_streams(OracleBackedGen(oracle), [b], 0.1, 2.0, batch_size=16, causal_warmup=False)[0]
     assert torch.equal(both[1], solo)
+    gen2 = OracleBackedGen(oracle)
+    corpus.encode_streams(gen2, [a, b], 0.1, 2.0, batch_size=16)
+    assert (2, 30400) in gen2.calls and (2, 1600) not in gen2.calls    # one prefix window per file replaces the 19 warm-up launches
 
 
 def test_plan_stream_shapes():

@@ -165,6 +165,22 @@ def test_programmatic_dependent_launch_changes_nothing(bundle):
             assert torch.equal(a, b)
 
 
+def test_corpus_encode_causal_warmup_is_exact(bundle):
+    """corpus.encode_streams: warm-up chunks read from ONE prefix window (causality) == 19 growing windows, and the
+    whole stream == AudioTokenizer.chunked_tokenize_audio on the same engine."""
+    from realtime_codec_agent_b200 import corpus
+    name, spec, w, g, gen = bundle
+    streams = [torch.from_numpy(g["wav0"]).cuda(), torch.from_numpy(g["wav1"][:36800 + 700]).cuda(),
+               torch.from_numpy(g["wav0"][:1600 * 7]).cuda()]
+    fast = corpus.encode_streams(gen, streams, 0.1, 2.0, batch_size=16, fuse_batches=2)
+    slow = corpus.encode_streams(gen, streams, 0.1, 2.0, batch_size=16, causal_warmup=False)
+    for a, b in zip(fast, slow):
+        assert torch.equal(a, b)
+    tok = pkg.AudioTokenizer(codec_model=gen, device="cuda")
+    s = tok.chunked_tokenize_audio(streams[1].cpu().numpy(), 0.1)
+    assert np.array_equal(fast[1].cpu().numpy(), np.array([ord(c) - tok.unicode_offset for c in s]))
+
+
 def test_unaligned_window_stride_falls_back(bundle):
     name, spec, w, g, gen = bundle
     wav = torch.from_numpy(g["wav0"]).cuda()
