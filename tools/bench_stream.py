@@ -43,11 +43,33 @@ def run(tok, chunk_secs, steps, warm):
             "decode_ms_per_frame_p50": float(np.percentile(dec_ms, 50)) / frames}
 
 
+def run_emit(tok, steps, warm, chunk_secs=0.1, target_rms=0.05):
+    """The agent's output step (realtime_agent_v2.py:556-579) on 0.1 s chunks: OutputChunkEmitter.emit = decoder +
+    pad_or_trim + normalize_audio_rms + smooth_join in ONE engine call, wall clock around the Python call."""
+    n = int(chunk_secs * 16000)
+    wav = pkg.synth_audio((steps + warm + 5) * n, seed=98).numpy()
+    tok.reset_context()
+    strings = [tok.tokenize_audio(wav[i * n:(i + 1) * n]) for i in range(steps + warm)]
+    tok.reset_context()
+    em = pkg.OutputChunkEmitter(tok, chunk_secs, 0.02, target_rms)
+    ms = []
+    for i, s in enumerate(strings):
+        t0 = time.perf_counter()
+        out = em.emit(s)
+        t1 = time.perf_counter()
+        assert out.shape == (n,)
+        if i >= warm:
+            ms.append((t1 - t0) * 1e3)
+    return {"chunk_secs": chunk_secs, "steps": steps, "target_volume_rms": target_rms,
+            "emit_wall_ms": {"p50": float(np.percentile(ms, 50)), "p90": float(np.percentile(ms, 90)), "p99": float(np.percentile(ms, 99))}}
+
+
 def main(steps=2000):
     spec = pkg.DEFAULT_SPEC
     gen = pkg.B200Generator(spec, pkg.init_random_weights(spec, seed=0), device="cuda")
     tok = pkg.AudioTokenizer(codec_model=gen, device="cuda")
-    out = {"frame_20ms": run(tok, 0.02, steps, 120), "chunk_100ms": run(tok, 0.1, max(200, steps // 4), 30)}
+    out = {"frame_20ms": run(tok, 0.02, steps, 120), "chunk_100ms": run(tok, 0.1, max(200, steps // 4), 30),
+           "emit_chain_100ms": run_emit(tok, max(200, steps // 4), 30)}
     print(json.dumps(out))
     return out
 
