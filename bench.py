@@ -293,6 +293,26 @@ def main():
                 "reference_equivalent_tflop_per_step_per_gpu": windows * spec.encode_flops(100) / 1e12,
                 "codes_checksum": int(sum(int(c.sum().item()) for c in codes) % (1 << 31))}
         if world == 1:
+            try:                                      # the decode half of the path at the offline batch shape
+                ctx = torch.stack([c[:25600] for c in codes]).reshape(-1, 100)[:1024].contiguous()    # 1024 windows x 100 codes
+                gen.decode(ctx)
+                torch.cuda.synchronize()
+                d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                gen.profile_begin()
+                d0.record()
+                for _ in range(5):
+                    gen.decode(ctx)
+                d1.record()
+                torch.cuda.synchronize()
+                dprof = gen.profile_end()
+                dms = d0.elapsed_time(d1) / 5
+                line["decode"] = {"value": ctx.shape[0] * 2.0 / (dms / 1e3), "unit": "audio-s/s", "ms_per_launch": dms,
+                                  "config": "mc_decode of 1024 windows x 100 codes -> 1024 x 2.0 s of waveform (every sample kept), "
+                                            "codes resident in HBM",
+                                  "gemm_TFLOPs": dprof["gemm"]["flops"] / (dprof["gemm"]["ms"] / 1e3) / 1e12 if dprof["gemm"]["ms"] else None,
+                                  "class_ms_per_launch": {k: v["ms"] / 5 for k, v in dprof.items()}}
+            except Exception as ex:
+                line["decode"] = {"error": repr(ex)}
             try:                                      # BASELINE metric, second half: p50 streaming decode ms/frame
                 from tools.bench_stream import run as stream_run, run_emit
                 tok = pkg.AudioTokenizer(codec_model=gen, device=dev)

@@ -448,7 +448,10 @@ attention_window_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, cons
 //     128 x 128.
 //   * a thread's live P columns depend only on its row, so the P tiles are zeroed ONCE and each item
 //     writes only its 64 live columns (128 B per row instead of 320 B).
-//   warps 0-3 / 4-7  softmax + output of slot 0 / 1     warp 8  TMA producer     warp 9  MMA issuer
+//   * single-tile windows run THREE compute slots (three softmax groups): a slot needs only NKV = 128 TMEM columns
+//     because O = P*V is accumulated over the slot's own S columns (dead once P is written), and the per-item
+//     chain S-MMA -> tcgen05.ld -> softmax -> P*V -> tcgen05.ld -> store is latency, not throughput.
+//   warps 4g..4g+3  softmax + output of slot g     warp 4*slots  TMA producer     warp 4*slots+1  MMA issuer
 //   kv_full[st] (tx) / kv_free[st] (commit after P*V)    s_full, p_full, o_full, slot_free per slot
 // Arithmetic (mask, ex2, ascending-key row sum, bf16 P, 16-key UMMA groups) is v2's, so results are
 // bit-identical to v2 and independent of where a window was cut for dead-output elimination.
@@ -459,28 +462,36 @@ struct Att3Cfg {
   static constexpr int kStageBytes = ATT_SMEM_Q + 2 * NKV * 128;   // Q + K + V
   static constexpr int kPAtoms = (NKV + 63) / 64;
   static constexpr int kPBytes = kPAtoms * ATT_BQ * 128;
-  static constexpr int kStages = (NKV == 128) ? 3 : 2;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kPBytes + 256 + 1024;
+  // compute slots (one softmax group of 4 warps, one P tile and NKV TMEM columns each; O = P*V is accumulated over
+  // the slot's own S columns, which are dead once P has been written) and TMA stages
+  static constexpr int kSlots = (NKV == 128) ? 3 : 2;
+  static constexpr int kStages = 2;
+  static constexpr int kThreads = (4 * kSlots + 2) * 32;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kSlots * kPBytes + 256 + 1024;
+  static_assert(kSlots * NKV <= 512, "TMEM columns");
+  static_assert(kSmemBytes <= 232448, "shared memory");
 };
 
 template <int NKV>
-__global__ void __launch_bounds__(ATT2_THREADS, 1)
+__global__ void __launch_bounds__(Att3Cfg<NKV>::kThreads, 1)
 attention_window_sm100_v3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                                  __nv_bfloat16* __restrict__ out, int B, int F, int H, int wl, int out_rows,
                                  float scale_log2e) {
   using Cfg = Att3Cfg<NKV>;
   constexpr int NST = Cfg::kStages;
+  constexpr int NSL = Cfg::kSlots;
+  constexpr int TMA_WARP = 4 * NSL, MMA_WARP = 4 * NSL + 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* p_base = smem + NST * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_base + 2 * Cfg::kPBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_base + NSL * Cfg::kPBytes);
   uint64_t* kv_full = bars;             // [NST]
   uint64_t* kv_free = bars + NST;       // [NST]
-  uint64_t* s_full = bars + 2 * NST;    // [2]
-  uint64_t* p_full = s_full + 2;        // [2]
-  uint64_t* o_full = p_full + 2;        // [2]
-  uint64_t* slot_free = o_full + 2;     // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(slot_free + 2);
+  uint64_t* s_full = bars + 2 * NST;    // [NSL]
+  uint64_t* p_full = s_full + NSL;      // [NSL]
+  uint64_t* o_full = p_full + NSL;      // [NSL]
+  uint64_t* slot_free = o_full + NSL;   // [NSL]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(slot_free + NSL);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = H * 64;
@@ -498,7 +509,7 @@ attention_window_sm100_v3_kernel(const __grid_constant__ CUtensorMap map_q, cons
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_free[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NSL; ++s) {
       mbar_init(&s_full[s], 1);
       mbar_init(&p_full[s], 4);
       mbar_init(&o_full[s], 1);
@@ -506,12 +517,12 @@ attention_window_sm100_v3_kernel(const __grid_constant__ CUtensorMap map_q, cons
     }
     fence_mbar_init();
   }
-  if (warp == 9) {
+  if (warp == MMA_WARP) {
     tmem_alloc(tmem_ptr, ATT2_TMEM_COLS);
     tmem_relinquish();
   }
   // P tiles start as zeros; only live columns are ever rewritten
-  for (int i = threadIdx.x; i < 2 * Cfg::kPBytes / 16; i += ATT2_THREADS)
+  for (int i = threadIdx.x; i < NSL * Cfg::kPBytes / 16; i += Cfg::kThreads)
     reinterpret_cast<uint4*>(p_base)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   pdl_launch_dependents();
@@ -521,7 +532,7 @@ attention_window_sm100_v3_kernel(const __grid_constant__ CUtensorMap map_q, cons
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();
 
-  if (warp == 8) {
+  if (warp == TMA_WARP) {
     if (lane == 0) {
       for (int it = 0; it < my_items; ++it) {
         const int item = blockIdx.x + it * gridDim.x;
@@ -539,24 +550,26 @@ attention_window_sm100_v3_kernel(const __grid_constant__ CUtensorMap map_q, cons
         tma_load_2d(stage + ATT_SMEM_Q + NKV * 128, &map_kv, &kv_full[st], 2 * d + h * 64, row_q - Cfg::kHalo);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == MMA_WARP) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, NKV, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, 64, 0, 1);
-      // slot s serves items s, s+2, ...: S(it) -> P*V(it) -> S(it+2) ...; the single issuing thread polls both
-      // slots and issues whatever is ready, so one slot's S overlaps the other's softmax.
-      int cur[2] = {0, 1};
-      bool need_pv[2] = {false, false};
+      // slot s serves items s, s+NSL, ...: S(it) -> P*V(it) -> S(it+NSL) ...; the single issuing thread polls all
+      // slots and issues whatever is ready, so one slot's MMAs overlap the others' softmax.
+      int cur[NSL];
+      bool need_pv[NSL];
+#pragma unroll
+      for (int s = 0; s < NSL; ++s) { cur[s] = s; need_pv[s] = false; }
       int remaining = 2 * my_items;
       const long long t0 = clock64();
       while (remaining > 0) {
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NSL; ++s) {
           const int it = cur[s];
           if (it >= my_items) continue;
           const int st = it % NST;
           const uint32_t st_use = (it / NST) & 1;
-          const uint32_t use = (it >> 1) & 1;
+          const uint32_t use = (it / NSL) & 1;
           uint8_t* stage = smem + st * Cfg::kStageBytes;
           if (!need_pv[s]) {
             if (!mbar_try_wait(&slot_free[s], use ^ 1)) continue;   // previous item of this slot read its S and O
@@ -565,7 +578,7 @@ attention_window_sm100_v3_kernel(const __grid_constant__ CUtensorMap map_q, cons
             const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(stage), 1024, 16);
             const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(stage + ATT_SMEM_Q), 1024, 16);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + s * 256, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+            for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + s * NKV, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
             umma_commit(&s_full[s]);
             need_pv[s] = true;
             --remaining;
@@ -578,12 +591,12 @@ attention_window_sm100_v3_kernel(const __grid_constant__ CUtensorMap map_q, cons
             for (int k = 0; k < NKV / 16; ++k) {
               const uint64_t pdesc = umma_smem_desc_sw128(smem_u32(sP + (k >> 2) * (ATT_BQ * 128)) + (k & 3) * 32, 1024, 16);
               const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sV) + k * 2048, 1024, 1024);
-              umma_bf16_ss(tmem_base + s * 256 + NKV, pdesc, vdesc, idesc_o, k != 0);
+              umma_bf16_ss(tmem_base + s * NKV, pdesc, vdesc, idesc_o, k != 0);   // O over the slot's (dead) S columns
             }
             umma_commit(&o_full[s]);
             umma_commit(&kv_free[st]);     // Q, K and V of this stage are consumed once these MMAs retire
             need_pv[s] = false;
-            cur[s] += 2;
+            cur[s] += NSL;
             --remaining;
           }
         }
@@ -599,13 +612,13 @@ attention_window_sm100_v3_kernel(const __grid_constant__ CUtensorMap map_q, cons
     const int r = q * 32 + lane;               // query row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     uint8_t* sP = p_base + s * Cfg::kPBytes;
-    const uint32_t tmem_s = tmem_base + s * 256;
-    const uint32_t tmem_o = tmem_s + NKV;
+    const uint32_t tmem_s = tmem_base + s * NKV;
+    const uint32_t tmem_o = tmem_s;            // P*V accumulates over S, which every warp has finished reading by then
     // rows of this warp see key columns [col_base, col_base + 64); without a halo the first 32 of warp 0 do not exist
     const int col_base = q * 32 + Cfg::kHalo - 32;
-    for (int it = s; it < my_items; it += 2) {
+    for (int it = s; it < my_items; it += NSL) {
       const int item = blockIdx.x + it * gridDim.x;
-      const uint32_t use = (it >> 1) & 1;
+      const uint32_t use = (it / NSL) & 1;
       const int qt = first_tile + item % kept_tiles;
       const int h = (item / kept_tiles) % H;
       const int b = item / (kept_tiles * H);
@@ -694,7 +707,7 @@ attention_window_sm100_v3_kernel(const __grid_constant__ CUtensorMap map_q, cons
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, ATT2_TMEM_COLS);
   }
@@ -719,7 +732,7 @@ inline int launch_attention_sm100_v3_nkv(mc_handle* h, const bf16* qkv, bf16* ou
   const long long items = (long long)B * s.n_heads * (q_tiles - (F - out_rows) / ATT_BQ);
   if (items > INT_MAX) return h->fail(MC_ERR_ARG, "attention: too many tiles");
   const int grid = (int)std::min<long long>(items, h->num_sms);
-  mc_launch(h, attention_window_sm100_v3_kernel<NKV>, dim3(grid), dim3(ATT2_THREADS), Cfg::kSmemBytes, stream, *mq, *mkv, out, B, F,
+  mc_launch(h, attention_window_sm100_v3_kernel<NKV>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, *mq, *mkv, out, B, F,
             s.n_heads, s.window_left, out_rows, 0.125f * 1.4426950408889634f);
   MC_LAUNCH_CHECK(h, "attention_window_sm100_v3_kernel");
   return MC_OK;
