@@ -560,6 +560,7 @@ attention_window_sm100_v3_kernel(const __grid_constant__ CUtensorMap map_q, cons
       bool need_pv[NSL];
 #pragma unroll
       for (int s = 0; s < NSL; ++s) { cur[s] = s; need_pv[s] = false; }
+      int next_s = 0;
       int remaining = 2 * my_items;
       const long long t0 = clock64();
       while (remaining > 0) {
@@ -572,6 +573,9 @@ attention_window_sm100_v3_kernel(const __grid_constant__ CUtensorMap map_q, cons
           const uint32_t use = (it / NSL) & 1;
           uint8_t* stage = smem + st * Cfg::kStageBytes;
           if (!need_pv[s]) {
+            // S steps are issued strictly in item order: a parity wait is only unambiguous one phase ahead, and with
+            // fewer TMA stages than slots an out-of-order poll of kv_full[st] would see the PREVIOUS fill's phase
+            if (it != next_s) continue;
             if (!mbar_try_wait(&slot_free[s], use ^ 1)) continue;   // previous item of this slot read its S and O
             if (!mbar_try_wait(&kv_full[st], st_use)) continue;
             tc_fence_after();
@@ -581,6 +585,7 @@ attention_window_sm100_v3_kernel(const __grid_constant__ CUtensorMap map_q, cons
             for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + s * NKV, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
             umma_commit(&s_full[s]);
             need_pv[s] = true;
+            ++next_s;
             --remaining;
           } else {
             if (!mbar_try_wait(&p_full[s], use)) continue;
