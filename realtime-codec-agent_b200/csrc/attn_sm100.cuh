@@ -448,9 +448,9 @@ attention_window_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, cons
 //     128 x 128.
 //   * a thread's live P columns depend only on its row, so the P tiles are zeroed ONCE and each item
 //     writes only its 64 live columns (128 B per row instead of 320 B).
-//   * single-tile windows run THREE compute slots (three softmax groups): a slot needs only NKV = 128 TMEM columns
-//     because O = P*V is accumulated over the slot's own S columns (dead once P is written), and the per-item
-//     chain S-MMA -> tcgen05.ld -> softmax -> P*V -> tcgen05.ld -> store is latency, not throughput.
+//   * a compute slot needs only NKV TMEM columns: O = P*V is accumulated over the slot's own S columns (dead once
+//     P is written).  The slot / stage counts are template constants (Att3Cfg); a 3-slot x 2-stage variant was
+//     measured slower than 2 x 3 (see Att3Cfg).
 //   warps 4g..4g+3  softmax + output of slot g     warp 4*slots  TMA producer     warp 4*slots+1  MMA issuer
 //   kv_full[st] (tx) / kv_free[st] (commit after P*V)    s_full, p_full, o_full, slot_free per slot
 // Arithmetic (mask, ex2, ascending-key row sum, bf16 P, 16-key UMMA groups) is v2's, so results are
@@ -464,8 +464,10 @@ struct Att3Cfg {
   static constexpr int kPBytes = kPAtoms * ATT_BQ * 128;
   // compute slots (one softmax group of 4 warps, one P tile and NKV TMEM columns each; O = P*V is accumulated over
   // the slot's own S columns, which are dead once P has been written) and TMA stages
-  static constexpr int kSlots = (NKV == 128) ? 3 : 2;
-  static constexpr int kStages = 2;
+  // measured at M = 102 400: 2 slots x 3 stages 1.46 ms per layer-launch set, 3 slots x 2 stages 1.81 ms — the
+  // depth of the load ring matters more than a third softmax group, and both do not fit in 227 KB
+  static constexpr int kSlots = 2;
+  static constexpr int kStages = (NKV == 128) ? 3 : 2;
   static constexpr int kThreads = (4 * kSlots + 2) * 32;
   static constexpr int kSmemBytes = kStages * kStageBytes + kSlots * kPBytes + 256 + 1024;
   static_assert(kSlots * NKV <= 512, "TMEM columns");
