@@ -1,0 +1,118 @@
+"""GPU (B200): edge cases of the C-ABI path — empty, one-sample, ragged and maximum-size inputs, clamps and error
+returns (never a crash or a hang), and the host tokenizer's edge behaviour on the native engine against the same
+calls on the CPU oracle model (lengths / exceptions; audio_tokenizer.py:67-149)."""
+import numpy as np
+import pytest
+import torch
+
+import realtime_codec_agent_b200 as pkg
+from oracle.magicodec_oracle import OracleGenerator
+from realtime_codec_agent_b200._native import McError
+
+pytestmark = pytest.mark.gpu
+MAXPOS = 512
+
+
+@pytest.fixture(scope="module")
+def gen():
+    return pkg.B200Generator(pkg.TINY_SPEC, pkg.init_random_weights(pkg.TINY_SPEC, seed=0), device="cuda", max_positions=MAXPOS)
+
+
+def test_encode_length_edges(gen):
+    wav = pkg.synth_audio(320 * MAXPOS + 10, device="cuda")
+    assert gen.encode(wav[None, :1]).shape == (1, 1)                      # one sample -> one (zero-padded) frame
+    assert gen.encode(wav[None, :319]).shape == (1, 1)
+    assert gen.encode(wav[None, :321]).shape == (1, 2)
+    full = gen.encode(wav[None, :320 * MAXPOS])                           # exactly the RoPE table
+    assert full.shape == (1, MAXPOS) and int(full.min()) >= 0 and int(full.max()) < gen.codebook_size
+    with pytest.raises(McError, match="exceed RoPE table"):
+        gen.encode(wav[None, :320 * MAXPOS + 1])
+    with pytest.raises(McError):
+        gen.encode(wav[None, :0])                                         # empty
+    # keep_last_frames beyond the window clamps to "all"; 0 means all
+    a = gen.encode(wav[None, :3200], keep_last_frames=999)
+    assert torch.equal(a, gen.encode(wav[None, :3200]))
+    # causality: a prefix's frames equal the longer window's first frames (what corpus.encode_streams relies on)
+    assert torch.equal(gen.encode(wav[None, :32000])[:, :37], gen.encode(wav[None, :320 * 37]))
+    # right zero padding == explicit zeros (pad_audio)
+    ragged = wav[:1000]
+    padded = torch.cat([ragged, torch.zeros(280, device="cuda")])
+    assert torch.equal(gen.encode(ragged[None]), gen.encode(padded[None]))
+
+
+def test_encode_batch_and_silence(gen):
+    sil = torch.zeros(3, 6400, device="cuda")
+    c = gen.encode(sil)
+    assert c.shape == (3, 20) and torch.equal(c[0], c[1]) and torch.equal(c[1], c[2])
+    big = pkg.synth_audio(1600 * 700 + 32000, device="cuda")
+    many = gen.encode(big, keep_last_frames=5, row_stride=1600, num_windows=700, window_samples=32000)   # M = 70 000 rows
+    assert many.shape == (700, 5)
+    assert torch.equal(many[123], gen.encode(big[None, 123 * 1600: 123 * 1600 + 32000], keep_last_frames=5)[0])
+    with pytest.raises(ValueError):
+        gen.encode(big, row_stride=1600, num_windows=701 + 20, window_samples=32000)
+
+
+def test_decode_edges(gen):
+    codes = torch.randint(0, gen.codebook_size, (2, 50), device="cuda")
+    full = gen.decode(codes)
+    assert full.shape == (2, 16000) and torch.isfinite(full).all()
+    assert gen.decode(codes[:, :1]).shape == (2, 320)                      # one frame
+    assert torch.equal(gen.decode(codes, keep_last_samples=10 ** 9), full)  # clamp
+    assert torch.equal(gen.decode(codes, keep_last_samples=1), full[:, -1:])
+    assert torch.equal(gen.decode(codes, keep_last_samples=321), full[:, -321:])
+    wild = codes.clone()
+    wild[0, 0], wild[1, 3] = -5, gen.codebook_size + 17                    # out-of-range codes are clamped, not read
+    lo = codes.clone(); lo[0, 0], lo[1, 3] = 0, gen.codebook_size - 1
+    assert torch.equal(gen.decode(wild), gen.decode(lo))
+    with pytest.raises(McError):
+        gen.decode(codes[:, :0])
+    with pytest.raises(McError, match="exceed RoPE table"):
+        gen.decode(torch.zeros(1, MAXPOS + 1, dtype=torch.int64, device="cuda"))
+    # causal decoder: the first samples do not depend on later codes
+    assert torch.equal(gen.decode(codes[:, :20]), full[:, :6400])
+
+
+def test_stream_session_limits(gen):
+    sess = gen.open_stream(2, 32000)
+    with pytest.raises(McError, match="exceeds the session capacity"):
+        sess.push_audio(np.zeros((2, 32001), np.float32), 1)
+    out = sess.push_audio(np.zeros((2, 32000), np.float32), 0)            # a chunk as long as the context, all frames
+    assert out.shape == (2, 100)
+    out = sess.push_audio(np.zeros((2, 1), np.float32), 1)                # one sample
+    assert out.shape == (2, 1)
+    sess.reset()
+    assert sess.push_audio(np.zeros((2, 320), np.float32), 0).shape == (2, 1)
+    with pytest.raises(McError):
+        sess.push_codes(np.zeros((2, 101), np.int64), 0)
+    wav = sess.push_codes(np.zeros((2, 100), np.int64), 0)
+    assert wav.shape == (2, 32000)
+    with pytest.raises(McError, match="mono"):
+        sess.set_emit(1600, 320, 0.0, 0.003, np.zeros(320, np.float32)); sess.push_codes_emit(np.zeros(5, np.int64))
+
+
+def test_native_tokenizer_edge_calls_match_the_cpu_model():
+    spec = pkg.TINY_SPEC
+    w = pkg.init_random_weights(spec, seed=0)
+    native = pkg.AudioTokenizer(codec_model=pkg.B200Generator(spec, w, device="cuda", max_positions=1024), device="cuda")
+    cpu = pkg.AudioTokenizer(codec_model=OracleGenerator(spec, w), device="cpu")
+    wav = pkg.synth_audio(8000).numpy()
+    for tok in (native, cpu):
+        with pytest.raises(RuntimeError):
+            tok.tokenize_audio(wav[:0])                                   # empty audio, empty context: both raise
+        tok.reset_context()
+    for chunk in (wav[:3200], wav[:0], wav[:100], (wav[:1600] * 32767).astype(np.int16), (8000, wav[:800]),
+                  np.stack([wav[:640], wav[640:1280]])):
+        a, b = native.tokenize_audio(chunk), cpu.tokenize_audio(chunk)
+        assert len(a) == len(b)                                           # int(secs * 50) chars; 0 -> whole context ([-0:])
+    assert native.tokenize_context.shape == cpu.tokenize_context.shape
+    for tok in (native, cpu):
+        tok.reset_context()
+        with pytest.raises(RuntimeError):
+            tok.detokenize_audio("")                                      # nothing to decode: both raise
+    s = cpu.tokenize_audio(wav[:3200])
+    (sr_a, wa), ha, pa = native.detokenize_audio(s, preroll_samples=123)
+    (sr_b, wb), hb, pb = cpu.detokenize_audio(s, preroll_samples=123)
+    assert (sr_a, wa.shape, ha, pa) == (sr_b, wb.shape, hb, pb)
+    (_, wa), _, pa = native.detokenize_audio("", preroll_samples=40)      # empty string with context: the [-0:] quirk
+    (_, wb), _, pb = cpu.detokenize_audio("", preroll_samples=40)
+    assert wa.shape == wb.shape and pa == pb
