@@ -563,7 +563,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
-    if (p.tma_store && lane == 0) tma_wait_group<0>();  // all bulk stores of this thread have landed
+    if (p.tma_store && lane == 0) tma_wait_group_read<0>();  // smem of every bulk store has been read; the writes land by grid end
   }
 
   __syncwarp();
@@ -723,7 +723,7 @@ gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
     }
-    if (p.tma_store && lane == 0) tma_wait_group<0>();
+    if (p.tma_store && lane == 0) tma_wait_group_read<0>();
   }
 
   __syncwarp();
