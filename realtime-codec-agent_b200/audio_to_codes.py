@@ -76,7 +76,7 @@ def output_dir(codes_path: str, codec_model: str, chunk_secs: float, context_sec
 def encode_corpus(gen, audio_path: str, codes_path: str, codec_model: str = "MagiCodec-50Hz-Base",
                   chunk_size_secs: float = 0.1, context_secs: float = 2.0, batch_size: int = 256, stereo: bool = False,
                   audio_filter: Optional[Sequence[str]] = None, rank: int = 0, world_size: int = 1,
-                  files_per_group: int = 8, overwrite: bool = False) -> List[corpus.ManifestEntry]:
+                  files_per_group: int = 8, overwrite: bool = False, fuse_batches: int = 4) -> List[corpus.ManifestEntry]:
     out_root = output_dir(codes_path, codec_model, chunk_size_secs, context_secs, stereo)
     files = get_files(audio_path, filters=audio_filter)
     sizes = [float(os.path.getsize(f)) for f in files]
@@ -94,7 +94,7 @@ def encode_corpus(gen, audio_path: str, codes_path: str, codec_model: str = "Mag
     def flush():
         if not pending:
             return
-        codes = corpus.encode_streams(gen, [p[3] for p in pending], chunk_size_secs, context_secs, batch_size)
+        codes = corpus.encode_streams(gen, [p[3] for p in pending], chunk_size_secs, context_secs, batch_size, fuse_batches)
         for (fid, ch, dst, stream), c in zip(pending, codes):
             np.save(dst, corpus.codes_to_array(c))
             n_win = -(-int(stream.numel()) // int(chunk_size_secs * gen.sample_rate))
