@@ -219,5 +219,29 @@ def diag_block_gemms():
             print(f"M{M} {name:28s} " + "  ".join(f"{k}: {v * 1e3:7.1f} us {fl / v / 1e9:6.0f} TF/s" for k, v in res.items()))
 
 
+def diag_skinny():
+    """Batch-1 GEMM shapes (M = 100): time per launch for each tile width, 300 back-to-back launches."""
+    gen = make_gen(pkg.DEFAULT_SPEC)
+    torch.manual_seed(0)
+    M = 100
+    for (N, K) in [(3072, 1024), (1024, 1024), (4096, 1024), (1024, 4096), (1024, 5120)]:
+        A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+        W = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
+        bias = torch.randn(N, device="cuda")
+        out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+        res = []
+        for bn in (64, 128, 256):
+            for _ in range(10):
+                gen.op_gemm(A, W, bias=bias, out=out, out_mode=0, block_n=bn)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(300):
+                gen.op_gemm(A, W, bias=bias, out=out, out_mode=0, block_n=bn)
+            e1.record()
+            torch.cuda.synchronize()
+            res.append(f"bn{bn}: {e0.elapsed_time(e1) / 300 * 1e3:6.1f} us")
+        print(f"M{M} N{N} K{K}  weights {N * K * 2 / 1e6:5.1f} MB  " + "  ".join(res))
+
+
 if __name__ == "__main__":
-    {"block": diag_block_gemms, "gemm": diag_gemm, "attn": diag_attn, "vq": diag_vq, "e2e": diag_e2e, "epi": diag_epi, "cyc": diag_epi_cycles}[sys.argv[1]]()
+    {"skinny": diag_skinny, "block": diag_block_gemms, "gemm": diag_gemm, "attn": diag_attn, "vq": diag_vq, "e2e": diag_e2e, "epi": diag_epi, "cyc": diag_epi_cycles}[sys.argv[1]]()
