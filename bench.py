@@ -137,10 +137,10 @@ def ncu_traffic():
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             t = json.load(f)
-        return {"bytes_per_launch": t["gemm"]["dram_bytes_per_launch"], "algorithmic_bytes_per_launch": t["gemm"]["algorithmic_bytes_per_launch"],
-                "launches_captured": t["gemm"]["launches"], "source": t["source"]}
+        return t["gemm"]["dram_bytes_per_launch"], {"algorithmic_bytes_per_launch": t["gemm"]["algorithmic_bytes_per_launch"],
+                                                    "launches_captured": t["gemm"]["launches"], "source": t["source"]}
     except Exception:
-        return None
+        return None, None
 
 
 # --------------------------------------------------------------------------------- GPU arm
@@ -271,7 +271,7 @@ def main():
         achieved = g["flops"] / (g["ms"] / 1e3) / 1e12 if g["ms"] > 0 else 0.0
         roofline = {"bound": "tensor", "kernel": "gemm_bf16_sm100_kernel (linears + implicit-GEMM convs)",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "peak_source": peak_src, "traffic": ncu_traffic(),
+                    "peak_source": peak_src, "traffic": ncu_traffic()[0], "traffic_detail": ncu_traffic()[1],
                     "launches": g["launches"], "avg_launch_ms": g["ms"] / max(1, g["launches"]),
                     "share_of_step": g["ms"] / prof_ms, "instrumented_ms_per_step": prof_ms / args.steps,
                     "other_classes_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
