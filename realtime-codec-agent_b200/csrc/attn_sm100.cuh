@@ -729,12 +729,7 @@ inline int launch_attention_sm100_v3_nkv(mc_handle* h, const bf16* qkv, bf16* ou
   const CUtensorMap *mq, *mkv;
   MC_TRY(mc_internal::get_map_2d_bf16(h, qkv, (uint64_t)3 * d, (uint64_t)B * F, 64, ATT_BQ, &mq));
   MC_TRY(mc_internal::get_map_2d_bf16(h, qkv, (uint64_t)3 * d, (uint64_t)B * F, 64, NKV, &mkv));
-  static bool attr_set = false;
-  if (!attr_set) {
-    MC_CUDA(h, cudaFuncSetAttribute(attention_window_sm100_v3_kernel<NKV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  MC_TRY(mc_allow_smem(h, attention_window_sm100_v3_kernel<NKV>, Cfg::kSmemBytes));
   const int q_tiles = (F + ATT_BQ - 1) / ATT_BQ;
   const long long items = (long long)B * s.n_heads * (q_tiles - (F - out_rows) / ATT_BQ);
   if (items > INT_MAX) return h->fail(MC_ERR_ARG, "attention: too many tiles");
@@ -758,12 +753,7 @@ inline int launch_attention_sm100_v2(mc_handle* h, const bf16* qkv, bf16* out, i
   const CUtensorMap *mq, *mkv;
   MC_TRY(mc_internal::get_map_2d_bf16(h, qkv, (uint64_t)3 * d, (uint64_t)B * F, 64, ATT_BQ, &mq));
   MC_TRY(mc_internal::get_map_2d_bf16(h, qkv, (uint64_t)3 * d, (uint64_t)B * F, 64, ATT_NKV, &mkv));
-  static bool attr_set = false;
-  if (!attr_set) {
-    MC_CUDA(h, cudaFuncSetAttribute(attention_window_sm100_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    ATT2_SMEM_BYTES));
-    attr_set = true;
-  }
+  MC_TRY(mc_allow_smem(h, attention_window_sm100_v2_kernel, ATT2_SMEM_BYTES));
   const int q_tiles = (F + ATT_BQ - 1) / ATT_BQ;
   const long long items = (long long)B * s.n_heads * (q_tiles - (F - out_rows) / ATT_BQ);
   if (items > INT_MAX) return h->fail(MC_ERR_ARG, "attention: too many tiles");
@@ -781,12 +771,7 @@ inline int launch_attention_sm100(mc_handle* h, const bf16* qkv, bf16* out, int 
   const CUtensorMap *mq, *mkv;
   MC_TRY(mc_internal::get_map_2d_bf16(h, qkv, (uint64_t)3 * d, (uint64_t)B * F, 64, ATT_BQ, &mq));
   MC_TRY(mc_internal::get_map_2d_bf16(h, qkv, (uint64_t)3 * d, (uint64_t)B * F, 64, ATT_NKV, &mkv));
-  static bool attr_set = false;
-  if (!attr_set) {
-    MC_CUDA(h, cudaFuncSetAttribute(attention_window_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    ATT_SMEM_BYTES));
-    attr_set = true;
-  }
+  MC_TRY(mc_allow_smem(h, attention_window_sm100_kernel, ATT_SMEM_BYTES));
   const long long blocks = (long long)((F + ATT_BQ - 1) / ATT_BQ) * s.n_heads * B;
   if (blocks > INT_MAX) return h->fail(MC_ERR_ARG, "attention: too many tiles");
   const dim3 grid((unsigned)blocks);

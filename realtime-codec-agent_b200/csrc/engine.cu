@@ -46,12 +46,7 @@ int launch_gemm_bn(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   p.rope_ld = h->spec.max_positions;
   p.rope_cos = c.rope_period > 0 ? h->ptr<float>("rope.cos") : nullptr;
   p.rope_sin = c.rope_period > 0 ? h->ptr<float>("rope.sin") : nullptr;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MC_CUDA(h, cudaFuncSetAttribute(gemm_bf16_sm100_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    GemmCfg<BN>::kSmemBytes));
-    attr_set = true;
-  }
+  MC_TRY(mc_allow_smem(h, gemm_bf16_sm100_kernel<BN>, GemmCfg<BN>::kSmemBytes));
   const int m_tiles = (c.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (c.N + BN - 1) / BN;
   const int grid = std::min(m_tiles * n_tiles, h->num_sms);
   const double valid_rows = c.grp_in == INT_MAX ? (double)c.M : (double)c.M / c.grp_in * c.grp_valid;
@@ -67,12 +62,7 @@ template <int EPI>
 int launch_gemm_pair_epi(mc_handle* h, const GemmCall& c, const GemmParams& p, const CUtensorMap* ma, const CUtensorMap* mb,
                          const CUtensorMap* mo, int pairs, cudaStream_t stream) {
   constexpr int BN = 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MC_CUDA(h, cudaFuncSetAttribute(gemm2_bf16_sm100_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Gemm2Cfg<BN>::kSmemBytes));
-    attr_set = true;
-  }
+  MC_TRY(mc_allow_smem(h, gemm2_bf16_sm100_kernel<BN, EPI>, Gemm2Cfg<BN>::kSmemBytes));
   mc_launch(h, gemm2_bf16_sm100_kernel<BN, EPI>, dim3(2 * pairs), dim3(GEMM_THREADS), Gemm2Cfg<BN>::kSmemBytes, stream, *ma, *mb, *mo, p);
   MC_LAUNCH_CHECK(h, "gemm2_bf16_sm100_kernel");
   return MC_OK;

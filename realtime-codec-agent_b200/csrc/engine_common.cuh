@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <climits>
 #include <map>
+#include <set>
 #include <string>
 #include <tuple>
 #include <unordered_map>
@@ -68,6 +69,8 @@ struct mc_handle {
   bool profiling = false;
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> event_pool;
+  // kernels whose dynamic-smem limit has been raised on THIS handle's device (the attribute is per device)
+  std::set<const void*> smem_configured;
   // workspace arena
   uint8_t* arena = nullptr;
   size_t arena_cap = 0;
@@ -124,6 +127,16 @@ struct McProfScope {
     h->prof.push_back(rec);
   }
 };
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize once per (handle, kernel)
+template <typename K>
+inline int mc_allow_smem(mc_handle* h, K kernel, int bytes) {
+  const void* key = reinterpret_cast<const void*>(kernel);
+  if (h->smem_configured.count(key)) return MC_OK;
+  MC_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  h->smem_configured.insert(key);
+  return MC_OK;
+}
 
 // Kernel launch with (optionally) the programmatic-stream-serialization attribute; the kernels call pdl_wait()
 // before touching anything a predecessor may have written.
