@@ -42,7 +42,7 @@ attention_window_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const _
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + ATT_SMEM_P);  // [0] tma, [1] S ready, [2] O ready
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   const int q_tiles = (F + ATT_BQ - 1) / ATT_BQ;
   const int q0 = (blockIdx.x % q_tiles) * ATT_BQ;
   const int h = (blockIdx.x / q_tiles) % H;

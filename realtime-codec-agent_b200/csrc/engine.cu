@@ -59,7 +59,7 @@ int launch_gemm_bn(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
 
 // CTA-pair kernel: 256 x 256 tiles on 74 clusters of two CTAs
 template <int EPI>
-int launch_gemm_pair_epi(mc_handle* h, const GemmCall& c, const GemmParams& p, const CUtensorMap* ma, const CUtensorMap* mb,
+int launch_gemm_pair_epi(mc_handle* h, const GemmParams& p, const CUtensorMap* ma, const CUtensorMap* mb,
                          const CUtensorMap* mo, int pairs, cudaStream_t stream) {
   constexpr int BN = 256;
   MC_TRY(mc_allow_smem(h, gemm2_bf16_sm100_kernel<BN, EPI>, Gemm2Cfg<BN>::kSmemBytes));
@@ -96,12 +96,12 @@ int launch_gemm_pair(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   // specialised epilogues (gemm_sm100.cuh): TMA-store output, bias, whole 256-column tiles, rope on 64-wide heads
   const bool fast_ok = h->fast_epilogue && tma_out && c.bias != nullptr && c.N % BN == 0;
   if (fast_ok && c.out_mode == OUT_BF16 && c.act == ACT_NONE && c.rope_period > 0 && c.rope_cols % 64 == 0)
-    return launch_gemm_pair_epi<EPI_ROPE_BF16>(h, c, p, ma, mb, mo, pairs, stream);
+    return launch_gemm_pair_epi<EPI_ROPE_BF16>(h, p, ma, mb, mo, pairs, stream);
   if (fast_ok && c.out_mode == OUT_BF16 && c.act == ACT_GELU_TANH && c.rope_period == 0)
-    return launch_gemm_pair_epi<EPI_GELU_BF16>(h, c, p, ma, mb, mo, pairs, stream);
+    return launch_gemm_pair_epi<EPI_GELU_BF16>(h, p, ma, mb, mo, pairs, stream);
   if (fast_ok && c.out_mode == OUT_F32_RESIDUAL && c.act == ACT_NONE && c.rope_period == 0)
-    return launch_gemm_pair_epi<EPI_RESID_F32>(h, c, p, ma, mb, mo, pairs, stream);
-  return launch_gemm_pair_epi<EPI_GENERIC>(h, c, p, ma, mb, mo, pairs, stream);
+    return launch_gemm_pair_epi<EPI_RESID_F32>(h, p, ma, mb, mo, pairs, stream);
+  return launch_gemm_pair_epi<EPI_GENERIC>(h, p, ma, mb, mo, pairs, stream);
 }
 
 int launch_gemm(mc_handle* h, const GemmCall& c, cudaStream_t stream) {

@@ -201,7 +201,7 @@ inline int launch_vq_sm100(mc_handle* h, const float* z, int n_items, int F, int
   const int row_tiles = (Mq + 127) / 128;
   int splits = (h->num_sms + row_tiles - 1) / row_tiles;
   splits = std::max(1, std::min(std::min(64, tiles_total), splits));
-  const CUtensorMap* mb;
+  const CUtensorMap* mb = nullptr;
   MC_TRY(mc_internal::get_map_2d_bf16(h, h->ptr<bf16>("vq.packed"), 64, (uint64_t)s.codebook_size, 64, VQ_BN, &mb));
   MC_TRY(mc_allow_smem(h, vq_argmin_sm100_kernel, VQ_SMEM_BYTES));
   mc_launch(h, vq_argmin_sm100_kernel, dim3(row_tiles, splits), dim3(VQ_THREADS), VQ_SMEM_BYTES, stream, *mb, z, Mq, F, keep,
