@@ -150,7 +150,8 @@ int mc_profile_end(mc_handle* h, double* ms, double* flops, double* bytes, int64
 /* Engine options (all default to 1): "shared_stem" — overlapping hop-aligned windows of one mc_encode call share a
  * single pass of the convolution stack (bit-identical results; 0 recomputes it per window, for A/B tests);
  * "gemm_pair" — cta_group::2 GEMM where the shape allows; "fast_epilogue" — its mode-specialised epilogues
- * (bit-identical to the generic one). */
+ * (bit-identical to the generic one); "attn_p_tmem" — attention keeps P in tensor memory (0: the shared-memory-P
+ * kernel, bit-identical); "pdl" — programmatic dependent launch between the kernels of a pass. */
 int mc_set_option(mc_handle* h, const char* key, int32_t value);
 /* impl: 0 = tensor-core kernels (default), 1 = SIMT cross-check kernels for attention / VQ; attention also
  * 2 = one-item-per-CTA tcgen05 kernel, 3 = two-slot persistent kernel without staged loads (A/B timing);

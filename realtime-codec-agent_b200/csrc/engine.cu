@@ -757,6 +757,7 @@ int mc_set_option(mc_handle* h, const char* key, int32_t value) {
   else if (k == "gemm_pair") h->gemm_pair = value != 0;
   else if (k == "fast_epilogue") h->fast_epilogue = value != 0;
   else if (k == "pdl") h->pdl = value != 0;
+  else if (k == "attn_p_tmem") h->attn_p_tmem = value != 0;
   else return h->fail(MC_ERR_ARG, "mc_set_option: unknown option '%s'", key);
   return MC_OK;
 }

@@ -62,6 +62,7 @@ struct mc_handle {
   int attn_impl = 0, vq_impl = 0;
   int gemm_pair = 1;  // use the cta_group::2 GEMM where the shape allows
   bool fast_epilogue = true;  // mode-specialised, software-pipelined epilogues in the CTA-pair GEMM
+  bool attn_p_tmem = true;    // attention: P through tensor memory (v4) instead of shared memory (v3)
   bool pdl = true;            // programmatic dependent launch between consecutive kernels of a pass
   bool shared_stem = true;  // overlapping hop-aligned windows share one pass of the conv stack (exact)
   // optional per-class device timing (bench.py's roofline): event pairs around each launch
