@@ -365,7 +365,7 @@ attention_window_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, cons
         sc[32 + j] = (j + 32 >= c_lo && j + 32 <= c_hi) ? __uint_as_float(raw1[j]) * scale_log2e : -INFINITY;
       }
 #pragma unroll
-      for (int j = 0; j < 64; ++j) mx = fmaxf(mx, sc[j]);
+      for (int j = 0; j < 64; j += 2) mx = fmax3(mx, sc[j], sc[j + 1]);
       const float mref = (mx == -INFINITY) ? 0.0f : mx;
       float sum = 0.0f;
       uint32_t pk[32];
@@ -654,7 +654,7 @@ attention_window_sm100_v3_kernel(const __grid_constant__ CUtensorMap map_q, cons
         sc[32 + j] = (j + 32 >= c_lo && j + 32 <= c_hi) ? __uint_as_float(raw1[j]) * scale_log2e : -INFINITY;
       }
 #pragma unroll
-      for (int j = 0; j < 64; ++j) mx = fmaxf(mx, sc[j]);
+      for (int j = 0; j < 64; j += 2) mx = fmax3(mx, sc[j], sc[j + 1]);
       const float mref = (mx == -INFINITY) ? 0.0f : mx;
       float sum = 0.0f;
       uint32_t pk[32];
@@ -912,7 +912,7 @@ attention_window_sm100_v4_kernel(const __grid_constant__ CUtensorMap map_q, cons
         sc[32 + j] = (j + 32 >= c_lo && j + 32 <= c_hi) ? __uint_as_float(raw1[j]) * scale_log2e : -INFINITY;
       }
 #pragma unroll
-      for (int j = 0; j < 64; ++j) mx = fmaxf(mx, sc[j]);
+      for (int j = 0; j < 64; j += 2) mx = fmax3(mx, sc[j], sc[j + 1]);
       const float mref = (mx == -INFINITY) ? 0.0f : mx;
       float sum = 0.0f;
       uint32_t pk[32];

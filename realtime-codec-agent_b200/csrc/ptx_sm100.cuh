@@ -14,6 +14,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// three-input maximum (one FMNMX3 on sm_100)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred = 0;
   asm volatile(

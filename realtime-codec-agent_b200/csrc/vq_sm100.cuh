@@ -157,9 +157,9 @@ vq_argmin_sm100_kernel(const __grid_constant__ CUtensorMap map_b, const float* _
         uint32_t raw[32];
         tmem_ld_32x32b_x32(taddr + c0, raw);
         tmem_ld_wait();
-        float cm = __uint_as_float(raw[0]);
+        float cm = fmaxf(__uint_as_float(raw[0]), __uint_as_float(raw[1]));
 #pragma unroll
-        for (int j = 1; j < 32; ++j) cm = fmaxf(cm, __uint_as_float(raw[j]));
+        for (int j = 2; j < 32; j += 2) cm = fmax3(cm, __uint_as_float(raw[j]), __uint_as_float(raw[j + 1]));
         if (cm > second) {  // this chunk can change the top two: exact ascending scan
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
