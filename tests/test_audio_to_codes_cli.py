@@ -49,3 +49,26 @@ def test_cli_layout_and_resume(tmp_path):
     assert audio_to_codes.encode_corpus(gen, str(tmp_path / "raw"), str(tmp_path / "codes"), stereo=True,
                                         audio_filter=["CallHome"]) == []
     assert len(gen.calls) == calls
+
+
+def test_two_ranks_partition_the_corpus(tmp_path):
+    """encode_audio_gpu_N.sh launches one process per GPU over the same corpus: with world_size 2 every file is encoded
+    by exactly one rank (LPT by size), outputs equal the single-rank run, and the manifests are disjoint."""
+    raw = tmp_path / "raw"
+    raw.mkdir()
+    for i, secs in enumerate((2.3, 0.7, 1.5, 3.1, 0.4)):
+        np.save(raw / f"clip{i}.npy", pkg.synth_audio(int(secs * 16000), file_id=30 + i).numpy())
+    gen = OracleBackedGen(OracleGenerator(pkg.TINY_SPEC, pkg.init_random_weights(pkg.TINY_SPEC, seed=0)))
+    solo = audio_to_codes.encode_corpus(gen, str(raw), str(tmp_path / "solo"), batch_size=16)
+    man = []
+    for rank in range(2):
+        man.append(audio_to_codes.encode_corpus(gen, str(raw), str(tmp_path / "duo"), batch_size=16, rank=rank, world_size=2))
+    assert sorted(e.file_id for m in man for e in m) == sorted(e.file_id for e in solo) == list(range(5))
+    assert not {e.file_id for e in man[0]} & {e.file_id for e in man[1]} and man[0] and man[1]
+    assert {e.rank for e in man[1]} == {1}
+    by_id = {e.file_id: e.crc32 for e in solo}
+    assert all(by_id[e.file_id] == e.crc32 for m in man for e in m)
+    for i in range(5):
+        a = np.load(tmp_path / "solo" / "MagiCodec-50Hz-Base" / "0.1s_2.0s" / "mono" / f"clip{i}_c0.npy")
+        b = np.load(tmp_path / "duo" / "MagiCodec-50Hz-Base" / "0.1s_2.0s" / "mono" / f"clip{i}_c0.npy")
+        assert np.array_equal(a, b)

@@ -270,6 +270,32 @@ def test_default_spec_shapes_and_determinism():
     assert emb.shape == (131072, 16) and torch.equal(emb, tok.get_codec_embeddings())
 
 
+def test_default_spec_parity_against_the_oracle():
+    """The BASELINE architecture itself (8+8 layers, d = 1024, 131 072 codes): engine vs the fp32 oracle computed here on
+    the host, same bars as the golden-vector tests (the 48 000-frame calibration is profiles/r01_parity_sweep_v10_*.jsonl)."""
+    spec = pkg.DEFAULT_SPEC
+    w = pkg.init_random_weights(spec, seed=0)
+    gen = pkg.B200Generator(spec, w, device="cuda")
+    oracle = OracleGenerator(spec, w)
+    torch.set_num_threads(os.cpu_count() or 1)
+    wav = torch.stack([pkg.synth_audio(32000, seed=55, file_id=i) for i in range(6)])
+    codes, _, z = gen.encode(wav.cuda(), return_margin=True, return_latents=True)
+    with torch.no_grad():
+        z_ref = oracle.encoder(oracle.pad_audio(wav))
+        z_q, idx_ref, margin = oracle.quantizer.inference(z_ref, return_margin=True)
+        rec_ref = oracle.decoder(z_q)[:, 0]
+    z_err = (z.cpu() - z_ref).abs().max().item()
+    clear = margin > EPS_MARGIN
+    rec = gen.decode(idx_ref.cuda()).cpu()
+    snr = _snr_db(rec_ref, rec)
+    _report("default", z_err=round(z_err, 4), near_tie_frac=round(1 - clear.float().mean().item(), 3),
+            agree_all=round((codes.cpu() == idx_ref).float().mean().item(), 3), snr_db=round(snr, 1))
+    assert z_err <= Z_TOL
+    assert torch.equal(codes.cpu()[clear], idx_ref[clear])
+    assert 1 - clear.float().mean().item() <= NEAR_TIE_MAX + 0.05
+    assert snr >= SNR_MIN_DB and (rec - rec_ref).abs().max().item() <= WAV_TOL * rec_ref.abs().max().item()
+
+
 def test_stream_session_equals_stateless_calls(bundle):
     """mc_stream_* (device-resident context + CUDA-graph replay) == re-sending the whole window."""
     name, spec, w, g, gen = bundle
