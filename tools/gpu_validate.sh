@@ -1,4 +1,5 @@
 #!/bin/bash
+# One gpurun call: the GPU test suite, the batch-1 latency check, one-batch class profile, bench.py (N=1).
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -q -m gpu --tb=short -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit=$?"
 tail -12 gpurun_out/pytest_gpu.log
