@@ -116,3 +116,42 @@ def test_native_tokenizer_edge_calls_match_the_cpu_model():
     (_, wa), _, pa = native.detokenize_audio("", preroll_samples=40)      # empty string with context: the [-0:] quirk
     (_, wb), _, pb = cpu.detokenize_audio("", preroll_samples=40)
     assert wa.shape == wb.shape and pa == pb
+
+
+def test_two_tokenizers_share_one_model_object(gen):
+    """clone_for_self_play hands the SAME model object to a second AudioTokenizer (realtime_agent_resources.py:46): two
+    tokenizers with different chunk sizes and channel counts interleave calls on one engine handle (shared workspace,
+    per-session CUDA graphs, workspace growth in between) and each must behave as if it were alone."""
+    wav = pkg.synth_audio(16000 * 4, file_id=9).numpy()
+    wav2 = np.stack([wav, pkg.synth_audio(16000 * 4, file_id=10).numpy()])
+
+    def run_alone(channels, n, audio):
+        tok = pkg.AudioTokenizer(codec_model=gen, num_channels=channels, device="cuda")
+        out = []
+        for s0 in range(0, 16000 * 3, n):
+            s = tok.tokenize_audio(audio[..., s0:s0 + n])
+            (_, w), _, _ = tok.detokenize_audio(s, preroll_samples=320)
+            out.append((s, w.copy()))
+        return out
+
+    alone_a, alone_b = run_alone(1, 320, wav), run_alone(2, 1600, wav2)
+    a = pkg.AudioTokenizer(codec_model=gen, num_channels=1, device="cuda")
+    b = pkg.AudioTokenizer(codec_model=gen, num_channels=2, device="cuda")
+    got_a, got_b = [], []
+    ia = ib = 0
+    while ia < len(alone_a) or ib < len(alone_b):
+        for _ in range(5):                                   # five 20 ms frames of A per 0.1 s chunk of B
+            if ia < len(alone_a):
+                s = a.tokenize_audio(wav[ia * 320:(ia + 1) * 320])
+                (_, w), _, _ = a.detokenize_audio(s, preroll_samples=320)
+                got_a.append((s, w.copy())); ia += 1
+        if ib < len(alone_b):
+            s = b.tokenize_audio(wav2[:, ib * 1600:(ib + 1) * 1600])
+            (_, w), _, _ = b.detokenize_audio(s, preroll_samples=320)
+            got_b.append((s, w.copy())); ib += 1
+        if ib == 7:                                          # a big one-shot call grows the shared workspace mid-stream
+            gen.encode(torch.zeros(64, 32000, device="cuda"))
+    for got, alone in ((got_a, alone_a), (got_b, alone_b)):
+        assert len(got) == len(alone)
+        for (s1, w1), (s2, w2) in zip(got, alone):
+            assert s1 == s2 and w1.shape == w2.shape and np.array_equal(w1, w2)
