@@ -112,6 +112,11 @@ int mc_stream_create(mc_handle* h, int32_t channels, int32_t context_samples, in
 int mc_stream_destroy(mc_stream* s);
 int mc_stream_reset(mc_stream* s);                      /* AudioTokenizer.reset_context, :44-46 (also forgets the emit chain's previous chunk) */
 int mc_stream_reset_part(mc_stream* s, int32_t audio, int32_t codes); /* drop only the audio and/or the code context */
+/* Upload a context WITHOUT computing anything: the session's audio (code) context becomes the last
+ * min(n, context) samples (frames) of the HOST array [C,n].  Re-seeds a session after a one-shot
+ * tokenize / detokenize call changed the host-side context (audio_tokenizer.py:72-74, 111-113). */
+int mc_stream_load_audio(mc_stream* s, const float* audio, int32_t n);
+int mc_stream_load_codes(mc_stream* s, const int64_t* codes, int32_t n);
 /* chunk fp32 [C,n]; codes_out int64 [C,keep_frames] (0 = every frame of the window). */
 int mc_stream_push_audio(mc_stream* s, const float* chunk, int32_t n, int32_t keep_frames, int64_t* codes_out,
                          int32_t* frames_out, mc_stream_t stream);

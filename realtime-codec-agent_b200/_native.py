@@ -54,6 +54,8 @@ SYMBOLS = {
     "mc_stream_destroy": (C.c_int, [_P]),
     "mc_stream_reset": (C.c_int, [_P]),
     "mc_stream_reset_part": (C.c_int, [_P, _I32, _I32]),
+    "mc_stream_load_audio": (C.c_int, [_P, _P, _I32]),
+    "mc_stream_load_codes": (C.c_int, [_P, _P, _I32]),
     "mc_stream_push_audio": (C.c_int, [_P, _P, _I32, _I32, _P, C.POINTER(_I32), _P]),
     "mc_stream_push_codes": (C.c_int, [_P, _P, _I32, _I32, _P, C.POINTER(_I32), _P]),
     "mc_stream_set_graphs": (C.c_int, [_P, _I32]),

@@ -21,6 +21,7 @@ _prep_audio_for_tokenization :203-215).  What differs is what runs underneath:
 from __future__ import annotations
 
 import math
+import threading
 from typing import Any, Optional, Tuple, Union
 
 import numpy as np
@@ -81,15 +82,19 @@ class AudioTokenizer:
         self.context_samples = int(self.context_secs * self.sampling_rate)
         self.context_frames = int(self.context_secs * self.framerate * self.num_channels)
         self._session = None
+        # One tokenizer may be shared by threads (tts_server.py:59,158 runs Flask with threaded=True on a single
+        # AudioTokenizer): the rolling contexts and the engine call that consumes them change together or not at all.
+        self._lock = threading.RLock()
         self.reset_context()
 
     # ------------------------------------------------------------------ state
     def reset_context(self):
-        self.tokenize_context = np.zeros((self.num_channels, 0), dtype=np.float32)
-        self.detokenize_context = ""
-        if getattr(self, "_session", None) is not None:
-            self._session.reset()
-        self._session_audio_ok = self._session_codes_ok = True      # device context mirrors the host context
+        with self._lock:
+            self.tokenize_context = np.zeros((self.num_channels, 0), dtype=np.float32)
+            self.detokenize_context = ""
+            if getattr(self, "_session", None) is not None:
+                self._session.reset()
+            self._session_audio_ok = self._session_codes_ok = True      # device context mirrors the host context
 
     def _stream_session(self):
         """Device-resident twin of the two contexts (native engine only), created on first use."""
@@ -109,11 +114,16 @@ class AudioTokenizer:
         total = wav.shape[-1]
         return "".join(self.tokenize_audio((sr, wav[..., s:s + step])) for s in range(0, total, step))
 
-    @torch.inference_mode()
     def tokenize_audio(self, audio: AudioLike) -> str:
+        with self._lock:
+            return self._tokenize_audio_locked(audio)
+
+    @torch.inference_mode()
+    def _tokenize_audio_locked(self, audio: AudioLike) -> str:
         new = self._prep_audio_for_tokenization(audio)
         n_new = new.shape[-1]
         C = self.num_channels
+        sess = self._stream_session() if self._native else None      # before the context changes: mirrors it from the start
         joined = np.concatenate((self.tokenize_context, new.reshape(C, -1)), axis=-1)
         keep = max(n_new, self.context_samples)
         self.tokenize_context = joined[..., -keep:]          # [-0:] keeps everything, as upstream
@@ -123,7 +133,6 @@ class AudioTokenizer:
 
         if self._native:
             frames_needed = -(-n_chars // C) if n_chars > 0 else 0          # 0 -> all frames
-            sess = self._stream_session()
             if self._session_audio_ok and 0 < n_new <= sess.cap_samples:
                 # steady state: only the new chunk crosses PCIe; the context lives in HBM
                 per_channel = sess.push_audio(new.reshape(C, -1), frames_needed)[:, None, :]
@@ -131,12 +140,9 @@ class AudioTokenizer:
                 window = torch.from_numpy(np.ascontiguousarray(self.tokenize_context)).to(self.device, non_blocking=True)
                 codes = self.codec_model.encode(window, keep_last_frames=frames_needed)  # [C,Fk] int64
                 per_channel = codes.cpu().numpy()[:, None, :]                   # [C,1,Fk]
-                # re-seed the device context with what the next call can still see
-                tail = self.tokenize_context[..., -self.context_samples:]
-                sess.reset_audio()
-                self._session_audio_ok = tail.shape[-1] > 0
-                if self._session_audio_ok:
-                    sess.push_audio(tail, 1)
+                # re-seed the device context with what the next call can still see (an upload, no compute)
+                sess.load_audio(self.tokenize_context[..., -self.context_samples:])
+                self._session_audio_ok = True
         else:
             window = torch.tensor(self.tokenize_context).to(self.device)
             with self._autocast():
@@ -156,10 +162,15 @@ class AudioTokenizer:
         return codes_to_chars(frame_major, self.codebook_size, unicode_offset=self.unicode_offset)
 
     # ----------------------------------------------------------------- decode
-    @torch.inference_mode()
     def detokenize_audio(self, audio_codes_str: str, preroll_samples: int = 0):
+        with self._lock:
+            return self._detokenize_audio_locked(audio_codes_str, preroll_samples)
+
+    @torch.inference_mode()
+    def _detokenize_audio_locked(self, audio_codes_str: str, preroll_samples: int = 0):
         audio_codes_str, end_hanging = self._drop_hanging_channel_codes(audio_codes_str)
         C = self.num_channels
+        sess = self._stream_session() if self._native else None
         self.detokenize_context += audio_codes_str
         keep = max(len(audio_codes_str), self.context_frames)
         self.detokenize_context = self.detokenize_context[-keep:]
@@ -171,18 +182,14 @@ class AudioTokenizer:
 
         if self._native:
             n_new_frames = len(audio_codes_str) // C
-            sess = self._stream_session()
             if self._session_codes_ok and 0 < n_new_frames <= sess.cap_frames:
                 new_codes = codes[:, codes.shape[1] - n_new_frames:]
                 wav = torch.from_numpy(sess.push_codes(new_codes, want))[None]      # [1,C,Tk]
             else:
                 dev_codes = torch.from_numpy(codes).to(self.device, non_blocking=True)
                 wav = self.codec_model.decode(dev_codes, keep_last_samples=want)[None].cpu()   # [1,C,Tk] fp32
-                tail = codes[:, -(self.context_frames // C):]
-                sess.reset_codes()
-                self._session_codes_ok = tail.shape[1] > 0
-                if self._session_codes_ok:
-                    sess.push_codes(tail, 1)
+                sess.load_codes(codes[:, -(self.context_frames // C):])
+                self._session_codes_ok = True
         else:
             dev_codes = torch.from_numpy(codes)[:, None, :].to(self.device)  # [C,1,F]
             with self._autocast():
@@ -201,26 +208,28 @@ class AudioTokenizer:
             raise RuntimeError("the fused emit chain needs the B200 engine")
         self._stream_session().set_emit(chunk_samples, fade_samples, target_rms, silence_rms_threshold, fade_in)
 
-    @torch.inference_mode()
     def detokenize_audio_emit(self, audio_codes_str: str):
         """detokenize_audio(str, preroll_samples=L) + pad_or_trim + normalize_audio_rms + smooth_join in one
         engine call.  Context bookkeeping is that of detokenize_audio (:105-113).  Returns
-        (float32[2*chunk + L] = emitted ++ cross-faded tail of the previous chunk ++ new history chunk, had_prev)."""
-        audio_codes_str, _ = self._drop_hanging_channel_codes(audio_codes_str)
-        before = self.detokenize_context
-        self.detokenize_context += audio_codes_str
-        keep = max(len(audio_codes_str), self.context_frames)
-        self.detokenize_context = self.detokenize_context[-keep:]
-        sess = self._stream_session()
-        if not self._session_codes_ok:
-            # device context out of step with the string (a one-shot decode ran in between): re-seed it
-            sess.reset_codes()
-            tail = before[-self.context_frames:]
-            if tail:
-                sess.push_codes(chars_to_codes(tail, 1, self.codebook_size, unicode_offset=self.unicode_offset), 1)
-            self._session_codes_ok = True
-        new_codes = chars_to_codes(audio_codes_str, 1, self.codebook_size, unicode_offset=self.unicode_offset)
-        return sess.push_codes_emit(new_codes)
+        (float32[2*chunk + L] = emitted ++ cross-faded tail of the previous chunk ++ new history chunk, had_prev).
+
+        The FIRST emitted chunk of a session needs an empty code context (the engine rejects it otherwise): with
+        a non-empty context the reference keeps an (n + L)-sample history chunk and its own length assert
+        (realtime_agent_v2.py:566-568) fires on the next chunk, so that state is unreachable upstream as well."""
+        with self._lock, torch.inference_mode():
+            audio_codes_str, _ = self._drop_hanging_channel_codes(audio_codes_str)
+            sess = self._stream_session()
+            before = self.detokenize_context
+            self.detokenize_context += audio_codes_str
+            keep = max(len(audio_codes_str), self.context_frames)
+            self.detokenize_context = self.detokenize_context[-keep:]
+            if not self._session_codes_ok:
+                # device context out of step with the string (a one-shot decode ran in between): re-seed it
+                tail = before[-self.context_frames:]
+                sess.load_codes(chars_to_codes(tail, 1, self.codebook_size, unicode_offset=self.unicode_offset))
+                self._session_codes_ok = True
+            new_codes = chars_to_codes(audio_codes_str, 1, self.codebook_size, unicode_offset=self.unicode_offset)
+            return sess.push_codes_emit(new_codes)
 
     # ---------------------------------------------------------- codec details
     @torch.inference_mode()

@@ -76,8 +76,11 @@ def encode_streams(gen, streams: Sequence[torch.Tensor], chunk_secs: float = 0.1
     (causal convs, causal windowed attention, window-relative RoPE), so frame t of a prefix equals frame t of the
     longer window: ONE full-frame encode of the longest warm-up window yields every warm-up chunk's codes instead
     of 19 launches of growing length per stream.  On the engine this is bit-identical (masked keys add exact
-    zeros; tested on the GPU against ``causal_warmup=False``)."""
+    zeros; tested on the GPU against ``causal_warmup=False``).  The shortcut is only taken when the spec really is
+    causal (``window_right == 0``): with any look-ahead a prefix frame would attend to audio beyond its own window,
+    so such specs go through the per-window path."""
     batch_size = batch_size * max(1, int(fuse_batches))
+    causal_warmup = causal_warmup and int(getattr(getattr(gen, "spec", None), "window_right", 0)) == 0
     sr, hop = gen.sample_rate, gen.hop
     framerate = sr / hop
     chunk = int(chunk_secs * sr)

@@ -636,6 +636,7 @@ int mc_set_tensor(mc_handle* h, const char* name, const void* dev_ptr, int64_t n
   if (!h || !name || !dev_ptr) return MC_ERR_ARG;
   Tensor t; t.p = dev_ptr; t.numel = numel;
   h->tensors[name] = t;
+  h->tensor_gen++;            // captured graphs carry the old pointer: sessions re-capture (run_or_replay)
   h->finalized = false;
   return MC_OK;
 }
@@ -758,6 +759,10 @@ int mc_set_option(mc_handle* h, const char* key, int32_t value) {
   else if (k == "fast_epilogue") h->fast_epilogue = value != 0;
   else if (k == "pdl") h->pdl = value != 0;
   else if (k == "attn_p_tmem") h->attn_p_tmem = value != 0;
+  else if (k == "max_positions") {   // rows of the re-registered rope.cos / rope.sin tables (B200Generator grows them on demand)
+    if (value < 1) return h->fail(MC_ERR_ARG, "mc_set_option: max_positions must be positive");
+    h->spec.max_positions = value;
+  }
   else return h->fail(MC_ERR_ARG, "mc_set_option: unknown option '%s'", key);
   return MC_OK;
 }
@@ -840,6 +845,11 @@ struct mc_stream {
 
 namespace {
 
+// everything a captured graph bakes in besides its key: the workspace arena and the registered tensors
+size_t handle_generation(const mc_handle* h) {
+  return reinterpret_cast<size_t>(h->arena) ^ h->arena_cap ^ (static_cast<size_t>(h->tensor_gen) << 48);
+}
+
 void stream_drop_graphs(mc_stream* s) {
   for (auto& kv : s->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -853,7 +863,7 @@ int run_or_replay(mc_stream* s, std::tuple<int, int, int, int, int> key, cudaStr
   mc_handle* h = s->h;
   if (!s->use_graphs || h->profiling) return body();
   auto& e = s->graphs[key];
-  const size_t gen = reinterpret_cast<size_t>(h->arena) ^ h->arena_cap;
+  const size_t gen = handle_generation(h);
   if (e.exec && e.arena_gen != gen) {
     cudaGraphExecDestroy(e.exec);
     e.exec = nullptr;
@@ -884,7 +894,7 @@ int run_or_replay(mc_stream* s, std::tuple<int, int, int, int, int> key, cudaStr
     s->use_graphs = false;
     return body();
   }
-  e.arena_gen = reinterpret_cast<size_t>(h->arena) ^ h->arena_cap;
+  e.arena_gen = handle_generation(h);
   MC_CUDA(h, cudaGraphLaunch(e.exec, stream));
   h->launches += 1;
   return MC_OK;
@@ -954,6 +964,37 @@ int mc_stream_reset_part(mc_stream* s, int32_t audio, int32_t codes) {
   if (!s) return MC_ERR_ARG;
   if (audio) s->audio_len = 0;
   if (codes) s->code_len = 0;
+  return MC_OK;
+}
+
+/* Context upload without compute: the session's audio (codes) context becomes the last min(n, context) samples
+ * (frames) of the HOST array [C, n].  Used to re-seed a session after a one-shot call changed the host-side context
+ * (AudioTokenizer keeps both in step); synchronous. */
+int mc_stream_load_audio(mc_stream* s, const float* audio, int32_t n) {
+  if (!s) return MC_ERR_ARG;
+  mc_handle* h = s->h;
+  MC_ENTER(h);
+  if (n < 0 || (n > 0 && !audio)) return h->fail(MC_ERR_ARG, "mc_stream_load_audio: bad arguments");
+  const int keep = std::min(n, s->ctx_samples);
+  MC_CUDA(h, cudaStreamSynchronize(s->own));
+  if (keep > 0)
+    MC_CUDA(h, cudaMemcpy2D(s->audio[s->acur], (size_t)s->cap_samples * 4, audio + (n - keep), (size_t)n * 4, (size_t)keep * 4,
+                            s->C, cudaMemcpyHostToDevice));
+  s->audio_len = keep;
+  return MC_OK;
+}
+
+int mc_stream_load_codes(mc_stream* s, const int64_t* codes, int32_t n) {
+  if (!s) return MC_ERR_ARG;
+  mc_handle* h = s->h;
+  MC_ENTER(h);
+  if (n < 0 || (n > 0 && !codes)) return h->fail(MC_ERR_ARG, "mc_stream_load_codes: bad arguments");
+  const int keep = std::min(n, s->ctx_frames);
+  MC_CUDA(h, cudaStreamSynchronize(s->own));
+  if (keep > 0)
+    MC_CUDA(h, cudaMemcpy2D(s->codes_ctx[s->ccur], (size_t)s->cap_frames * 8, codes + (n - keep), (size_t)n * 8, (size_t)keep * 8,
+                            s->C, cudaMemcpyHostToDevice));
+  s->code_len = keep;
   return MC_OK;
 }
 

@@ -59,6 +59,7 @@ struct mc_handle {
   std::unordered_map<std::string, Tensor> tensors;
   std::string err;
   int64_t launches = 0;
+  uint32_t tensor_gen = 0;    // bumped by mc_set_tensor
   int attn_impl = 0, vq_impl = 0;
   int gemm_pair = 1;  // use the cta_group::2 GEMM where the shape allows
   bool fast_epilogue = true;  // mode-specialised, software-pipelined epilogues in the CTA-pair GEMM

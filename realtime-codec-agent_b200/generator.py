@@ -11,7 +11,9 @@ owns the device buffers and the stream.  Nothing here falls back to PyTorch ops 
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import threading
 from typing import Dict, Optional
 
 import torch
@@ -141,6 +143,20 @@ class StreamSession:
     def reset_codes(self) -> None:
         self.gen._lib.mc_stream_reset_part(self._h, 0, 1)
 
+    def load_audio(self, audio) -> None:
+        """float32 [C,n] -> the session's audio context (its last `context` samples); no compute."""
+        np = self._np
+        audio = np.ascontiguousarray(audio, dtype=np.float32).reshape(self.channels, -1)
+        rc = self.gen._lib.mc_stream_load_audio(self._h, audio.ctypes.data, audio.shape[1])
+        nat.check(self.gen._lib, self.gen._handle, rc, "mc_stream_load_audio")
+
+    def load_codes(self, codes) -> None:
+        """int64 [C,n] -> the session's code context (its last `context` frames); no compute."""
+        np = self._np
+        codes = np.ascontiguousarray(codes, dtype=np.int64).reshape(self.channels, -1)
+        rc = self.gen._lib.mc_stream_load_codes(self._h, codes.ctypes.data, codes.shape[1])
+        nat.check(self.gen._lib, self.gen._handle, rc, "mc_stream_load_codes")
+
     def set_graphs(self, enabled: bool) -> None:
         self.gen._lib.mc_stream_set_graphs(self._h, 1 if enabled else 0)
 
@@ -151,9 +167,10 @@ class StreamSession:
         n = chunk.shape[1]
         out = np.empty((self.channels, self.cap_frames), dtype=np.int64)
         got = C.c_int32(0)
-        rc = self.gen._lib.mc_stream_push_audio(self._h, chunk.ctypes.data, n, keep_frames, out.ctypes.data, C.byref(got),
-                                                self.gen._stream())
-        nat.check(self.gen._lib, self.gen._handle, rc, "mc_stream_push_audio")
+        with self.gen._serial():
+            rc = self.gen._lib.mc_stream_push_audio(self._h, chunk.ctypes.data, n, keep_frames, out.ctypes.data, C.byref(got),
+                                                    self.gen._stream())
+            nat.check(self.gen._lib, self.gen._handle, rc, "mc_stream_push_audio")
         return out.reshape(-1)[: self.channels * got.value].reshape(self.channels, got.value)
 
     def push_codes(self, codes, keep_samples: int):
@@ -163,9 +180,10 @@ class StreamSession:
         n = codes.shape[1]
         out = np.empty((self.channels * self.cap_samples,), dtype=np.float32)
         got = C.c_int32(0)
-        rc = self.gen._lib.mc_stream_push_codes(self._h, codes.ctypes.data, n, keep_samples, out.ctypes.data, C.byref(got),
-                                                self.gen._stream())
-        nat.check(self.gen._lib, self.gen._handle, rc, "mc_stream_push_codes")
+        with self.gen._serial():
+            rc = self.gen._lib.mc_stream_push_codes(self._h, codes.ctypes.data, n, keep_samples, out.ctypes.data, C.byref(got),
+                                                    self.gen._stream())
+            nat.check(self.gen._lib, self.gen._handle, rc, "mc_stream_push_codes")
         return out[: self.channels * got.value].reshape(self.channels, got.value)
 
     def set_emit(self, chunk_samples: int, fade_samples: int, target_rms: float, silence_rms_threshold: float, fade_in) -> None:
@@ -185,9 +203,10 @@ class StreamSession:
         codes = np.ascontiguousarray(codes, dtype=np.int64).reshape(-1)
         out = np.empty((self._emit_floats,), dtype=np.float32)
         had = C.c_int32(0)
-        rc = self.gen._lib.mc_stream_push_codes_emit(self._h, codes.ctypes.data, codes.shape[0], out.ctypes.data, C.byref(had),
-                                                     self.gen._stream())
-        nat.check(self.gen._lib, self.gen._handle, rc, "mc_stream_push_codes_emit")
+        with self.gen._serial():
+            rc = self.gen._lib.mc_stream_push_codes_emit(self._h, codes.ctypes.data, codes.shape[0], out.ctypes.data, C.byref(had),
+                                                         self.gen._stream())
+            nat.check(self.gen._lib, self.gen._handle, rc, "mc_stream_push_codes_emit")
         return out, bool(had.value)
 
     def __del__(self):
@@ -209,6 +228,7 @@ class _Quantizer:
     def __init__(self, gen: "B200Generator"):
         self._gen = gen
         self.codebook = _Codebook(gen._dev["vq.codebook_raw"])
+        self._table_bf16 = None
 
     def codebook_proj(self, weight: torch.Tensor) -> torch.Tensor:
         """codebook_proj(codebook.weight) -> the cached projected table (audio_tokenizer.py:158,198).
@@ -217,7 +237,9 @@ class _Quantizer:
             raise NotImplementedError("B200Generator projects its own (frozen) codebook only")
         table = self._gen._dev["vq.codebook"]
         if torch.is_autocast_enabled("cuda"):
-            return table.to(BF16)
+            if self._table_bf16 is None:                       # cast once: the reference re-projects 131 072 rows per decode
+                self._table_bf16 = table.to(BF16)
+            return self._table_bf16
         return table
 
     def inference(self, z_e: torch.Tensor):
@@ -274,6 +296,12 @@ class B200Generator:
         nat.check(self._lib, self._handle, self._lib.mc_finalize(self._handle), "mc_finalize")
         self.quantizer = _Quantizer(self)
         self._last_encoded = None
+        # The handle owns ONE workspace arena and its sessions own captured graphs over it: calls on one handle are
+        # serialised on the host (threads: tts_server.py:158 runs Flask threaded on one tokenizer; two tokenizers on
+        # one model: realtime_agent_resources.py:41-49) and ordered on the device across streams.
+        self._lock = threading.RLock()
+        self._last_event = torch.cuda.Event()
+        self._last_stream = None
 
     # ---- nn.Module-ish surface used by AudioTokenizer.__init__ (:28)
     def eval(self):
@@ -296,6 +324,20 @@ class B200Generator:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    @contextlib.contextmanager
+    def _serial(self):
+        """Host lock + device ordering for one engine call: work queued on another stream by the previous call must
+        be finished with the shared workspace before this call's kernels touch it."""
+        with self._lock:
+            st = torch.cuda.current_stream(self.device)
+            if self._last_stream is not None and self._last_stream != st.cuda_stream:
+                st.wait_event(self._last_event)
+            try:
+                yield st
+            finally:
+                self._last_event.record(st)
+                self._last_stream = st.cuda_stream
+
     def frames_for(self, samples: int) -> int:
         return -(-samples // self.hop)
 
@@ -304,7 +346,27 @@ class B200Generator:
         return int(self._lib.mc_launch_count(self._handle))
 
     def open_stream(self, channels: int, context_samples: int, max_chunk_samples: int = 0) -> StreamSession:
-        return StreamSession(self, channels, context_samples, max(max_chunk_samples, context_samples))
+        cap = max(max_chunk_samples, context_samples)
+        self.ensure_positions(self.frames_for(cap))
+        return StreamSession(self, channels, context_samples, cap)
+
+    def ensure_positions(self, frames: int) -> None:
+        """Grow the RoPE tables so that inputs of `frames` frames are accepted (the reference's AudioTokenizer takes
+        any length: run_demo.py:55,109 encode / decode whole files in one call).  The new tables are registered under
+        the same names; captured stream graphs notice the changed tensor generation and re-capture."""
+        if frames <= self.max_positions:
+            return
+        new_max = 1 << (int(frames) - 1).bit_length()
+        cos, sin = rope_tables(new_max, self.spec.head_dim, self.spec.rope_base)
+        torch.cuda.synchronize(self.device)                       # nothing in flight reads the old tables
+        for name, t in (("rope.cos", cos), ("rope.sin", sin)):
+            dev = t.t().contiguous().to(self.device)
+            self._dev[name] = dev
+            rc = self._lib.mc_set_tensor(self._handle, name.encode(), dev.data_ptr(), dev.numel())
+            nat.check(self._lib, self._handle, rc, f"mc_set_tensor({name})")
+        self.set_option("max_positions", new_max)
+        nat.check(self._lib, self._handle, self._lib.mc_finalize(self._handle), "mc_finalize")
+        self.max_positions = new_max
 
     def set_debug_impl(self, attention: int = 0, vq: int = 0) -> None:
         nat.check(self._lib, self._handle, self._lib.mc_set_debug_impl(self._handle, attention, vq), "mc_set_debug_impl")
@@ -349,13 +411,15 @@ class B200Generator:
             if (B - 1) * ld + T > wav.numel():
                 raise ValueError("windows exceed the audio buffer")
         F = self.frames_for(T)
+        self.ensure_positions(F)
         keep = F if keep_last_frames <= 0 or keep_last_frames > F else keep_last_frames
         codes = torch.empty((B, keep), dtype=torch.int64, device=self.device)
         margin = torch.empty((B, keep), dtype=F32, device=self.device) if return_margin else None
         z_e = torch.empty((B, F, self.spec.codebook_dim), dtype=F32, device=self.device) if return_latents else None
-        rc = self._lib.mc_encode(self._handle, wav.data_ptr(), ld, B, T, keep, codes.data_ptr(), nat.ptr(margin),
-                                 nat.ptr(z_e), self._stream())
-        nat.check(self._lib, self._handle, rc, "mc_encode")
+        with self._serial():
+            rc = self._lib.mc_encode(self._handle, wav.data_ptr(), ld, B, T, keep, codes.data_ptr(), nat.ptr(margin),
+                                     nat.ptr(z_e), self._stream())
+            nat.check(self._lib, self._handle, rc, "mc_encode")
         if return_margin or return_latents:
             return codes, margin, z_e
         return codes
@@ -366,11 +430,13 @@ class B200Generator:
         if codes.dim() == 1:
             codes = codes[None]
         B, F = codes.shape
+        self.ensure_positions(F)
         total = F * self.hop
         keep = total if keep_last_samples <= 0 or keep_last_samples > total else keep_last_samples
         wav = torch.empty((B, keep), dtype=F32, device=self.device)
-        rc = self._lib.mc_decode(self._handle, codes.data_ptr(), B, F, keep, wav.data_ptr(), self._stream())
-        nat.check(self._lib, self._handle, rc, "mc_decode")
+        with self._serial():
+            rc = self._lib.mc_decode(self._handle, codes.data_ptr(), B, F, keep, wav.data_ptr(), self._stream())
+            nat.check(self._lib, self._handle, rc, "mc_decode")
         return wav
 
     def vq_search(self, z: torch.Tensor, return_margin: bool = False):
@@ -378,8 +444,9 @@ class B200Generator:
         M = z.shape[0]
         codes = torch.empty((M,), dtype=torch.int64, device=self.device)
         margin = torch.empty((M,), dtype=F32, device=self.device) if return_margin else None
-        rc = self._lib.mc_vq_search(self._handle, z.data_ptr(), M, codes.data_ptr(), nat.ptr(margin), self._stream())
-        nat.check(self._lib, self._handle, rc, "mc_vq_search")
+        with self._serial():
+            rc = self._lib.mc_vq_search(self._handle, z.data_ptr(), M, codes.data_ptr(), nat.ptr(margin), self._stream())
+            nat.check(self._lib, self._handle, rc, "mc_vq_search")
         return (codes, margin) if return_margin else codes
 
     def embed_distance(self, ids: torch.Tensor, vocab_start: int = 0, ref: Optional[torch.Tensor] = None,
@@ -393,9 +460,10 @@ class B200Generator:
         ref = None if ref is None else ref.to(self.device, F32).contiguous()
         dist = torch.empty((rows,), dtype=F32, device=self.device)
         mean = torch.empty((rows, self.spec.codebook_dim), dtype=F32, device=self.device) if want_mean else None
-        rc = self._lib.mc_embed_distance(self._handle, ids.data_ptr(), rows, n, int(vocab_start), nat.ptr(ref),
-                                         dist.data_ptr(), nat.ptr(mean), self._stream())
-        nat.check(self._lib, self._handle, rc, "mc_embed_distance")
+        with self._serial():
+            rc = self._lib.mc_embed_distance(self._handle, ids.data_ptr(), rows, n, int(vocab_start), nat.ptr(ref),
+                                             dist.data_ptr(), nat.ptr(mean), self._stream())
+            nat.check(self._lib, self._handle, rc, "mc_embed_distance")
         return (dist, mean) if want_mean else dist
 
     # ---- the reference wrapper's call sequence (audio_tokenizer.py:190-192, 198-200)
@@ -410,9 +478,11 @@ class B200Generator:
     def decoder(self, z_q: torch.Tensor) -> torch.Tensor:
         z = z_q.to(self.device, F32).contiguous()
         B, F = z.shape[0], z.shape[1]
+        self.ensure_positions(F)
         wav = torch.empty((B, F * self.hop), dtype=F32, device=self.device)
-        rc = self._lib.mc_decode_latents(self._handle, z.data_ptr(), B, F, 0, wav.data_ptr(), self._stream())
-        nat.check(self._lib, self._handle, rc, "mc_decode_latents")
+        with self._serial():
+            rc = self._lib.mc_decode_latents(self._handle, z.data_ptr(), B, F, 0, wav.data_ptr(), self._stream())
+            nat.check(self._lib, self._handle, rc, "mc_decode_latents")
         return wav[:, None, :]
 
     # ---- operator-level hooks (parity tests / profiling)

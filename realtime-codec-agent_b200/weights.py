@@ -109,13 +109,16 @@ def init_random_weights(spec: MagiCodecSpec, seed: int = 0) -> Dict[str, torch.T
 
 
 def save_checkpoint(path: str, spec: MagiCodecSpec, weights: Dict[str, torch.Tensor]) -> None:
+    """A plain dict of python scalars / lists and tensors: loadable with ``weights_only=True``."""
     import dataclasses
-    torch.save({"spec": dataclasses.asdict(spec), "weights": weights}, path)
+    s = {k: (list(v) if isinstance(v, tuple) else v) for k, v in dataclasses.asdict(spec).items()}
+    torch.save({"spec": s, "weights": {k: v.detach().cpu() for k, v in weights.items()}}, path)
 
 
 def load_checkpoint(path: str):
-    blob = torch.load(path, map_location="cpu", weights_only=False)
-    s = blob["spec"]
+    # weights_only: a checkpoint path comes from the caller or from $MAGICODEC_B200_CHECKPOINT; never unpickle code
+    blob = torch.load(path, map_location="cpu", weights_only=True)
+    s = dict(blob["spec"])
     for k in ("conv_channels", "conv_strides"):
         s[k] = tuple(s[k])
     spec = MagiCodecSpec(**s)

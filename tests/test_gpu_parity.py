@@ -270,30 +270,95 @@ def test_default_spec_shapes_and_determinism():
     assert emb.shape == (131072, 16) and torch.equal(emb, tok.get_codec_embeddings())
 
 
-def test_default_spec_parity_against_the_oracle():
-    """The BASELINE architecture itself (8+8 layers, d = 1024, 131 072 codes): engine vs the fp32 oracle computed here on
-    the host, same bars as the golden-vector tests (the 48 000-frame calibration is profiles/r01_parity_sweep_v10_*.jsonl)."""
+AGREE_ALL_MIN = 0.975      # fraction of ALL frames (near-ties included) whose code equals the fp32 oracle's; measured 0.981-0.987
+N_SAMPLE_WINDOWS = 48      # x 100 frames = 4 800 frames per spec under the driver
+
+
+def _sample_stats(codes, z, idx_ref, z_ref, margin):
+    dis = codes != idx_ref
+    return {"z_err_max": (z - z_ref).abs().max().item(), "z_err_rms": (z - z_ref).pow(2).mean().sqrt().item(),
+            "agree_all": 1.0 - dis.float().mean().item(),
+            "max_margin_of_disagreement": margin[dis].max().item() if dis.any() else 0.0,
+            "disagree_above_eps": int((dis & (margin > EPS_MARGIN)).sum())}
+
+
+@pytest.fixture(scope="module")
+def default_sample():
+    """4 800 frames of the BASELINE architecture (8+8 layers, d = 1024, 131 072 codes): the fp32 oracle on the host
+    cores, the engine, and the reference's OWN GPU numerics — the same oracle module run eagerly under
+    torch.autocast(bfloat16) on this B200 (audio_tokenizer.py:24,78-82: cuBLAS / cuDNN / SDPA in bf16)."""
     spec = pkg.DEFAULT_SPEC
     w = pkg.init_random_weights(spec, seed=0)
     gen = pkg.B200Generator(spec, w, device="cuda")
     oracle = OracleGenerator(spec, w)
     torch.set_num_threads(os.cpu_count() or 1)
-    wav = torch.stack([pkg.synth_audio(32000, seed=55, file_id=i) for i in range(6)])
+    wav = torch.stack([pkg.synth_audio(32000, seed=55, file_id=i) for i in range(N_SAMPLE_WINDOWS)])
     codes, _, z = gen.encode(wav.cuda(), return_margin=True, return_latents=True)
     with torch.no_grad():
         z_ref = oracle.encoder(oracle.pad_audio(wav))
         z_q, idx_ref, margin = oracle.quantizer.inference(z_ref, return_margin=True)
-        rec_ref = oracle.decoder(z_q)[:, 0]
-    z_err = (z.cpu() - z_ref).abs().max().item()
-    clear = margin > EPS_MARGIN
-    rec = gen.decode(idx_ref.cuda()).cpu()
-    snr = _snr_db(rec_ref, rec)
-    _report("default", z_err=round(z_err, 4), near_tie_frac=round(1 - clear.float().mean().item(), 3),
-            agree_all=round((codes.cpu() == idx_ref).float().mean().item(), 3), snr_db=round(snr, 1))
-    assert z_err <= Z_TOL
-    assert torch.equal(codes.cpu()[clear], idx_ref[clear])
+        rec_ref = oracle.decoder(z_q[:6])[:, 0]
+        eager = OracleGenerator(spec, w).cuda()
+        with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+            z_eager = eager.encoder(eager.pad_audio(wav.cuda()))
+            idx_eager_autocast = eager.quantizer.inference(z_eager)[1]          # distances in bf16 too (pure autocast)
+        idx_eager = eager.quantizer.inference(z_eager.float())[1]               # bf16 network, fp32 search
+    return {"spec": spec, "gen": gen, "codes": codes.cpu(), "z": z.cpu(), "z_ref": z_ref, "idx_ref": idx_ref, "margin": margin,
+            "rec_ref": rec_ref, "z_eager": z_eager.float().cpu(), "idx_eager": idx_eager.cpu(),
+            "idx_eager_autocast": idx_eager_autocast.cpu()}
+
+
+def test_default_spec_parity_against_the_oracle(default_sample):
+    """The BASELINE architecture itself: engine vs the fp32 oracle, same bars as the golden-vector tests, 4 800 frames
+    (the 48 000-frame calibration is profiles/r01_parity_sweep_v10_*.jsonl)."""
+    s = default_sample
+    st = _sample_stats(s["codes"], s["z"], s["idx_ref"], s["z_ref"], s["margin"])
+    clear = s["margin"] > EPS_MARGIN
+    rec = s["gen"].decode(s["idx_ref"][:6].cuda()).cpu()
+    snr = _snr_db(s["rec_ref"], rec)
+    _report("default", frames=s["idx_ref"].numel(), z_err=round(st["z_err_max"], 4),
+            near_tie_frac=round(1 - clear.float().mean().item(), 3), agree_all=round(st["agree_all"], 4),
+            max_margin_of_disagreement=round(st["max_margin_of_disagreement"], 4), snr_db=round(snr, 1))
+    assert s["idx_ref"].numel() >= 4000
+    assert st["z_err_max"] <= Z_TOL
+    assert torch.equal(s["codes"][clear], s["idx_ref"][clear])
+    assert st["agree_all"] >= AGREE_ALL_MIN
     assert 1 - clear.float().mean().item() <= NEAR_TIE_MAX + 0.05
-    assert snr >= SNR_MIN_DB and (rec - rec_ref).abs().max().item() <= WAV_TOL * rec_ref.abs().max().item()
+    assert snr >= SNR_MIN_DB and (rec - s["rec_ref"]).abs().max().item() <= WAV_TOL * s["rec_ref"].abs().max().item()
+
+
+def test_engine_agrees_with_the_oracle_at_least_as_well_as_the_reference_gpu_numerics(default_sample):
+    """Justifies EPS_MARGIN: the reference's own GPU path (eager bf16 autocast of the same network on the same B200)
+    disagrees with the fp32 oracle too.  The engine (bf16 multiplies, fp32 accumulation AND fp32 residual stream,
+    split-bf16 fp32-accurate search) must not be further from the oracle than that path is."""
+    s = default_sample
+    eng = _sample_stats(s["codes"], s["z"], s["idx_ref"], s["z_ref"], s["margin"])
+    ref = _sample_stats(s["idx_eager"], s["z_eager"], s["idx_ref"], s["z_ref"], s["margin"])
+    ref_ac = _sample_stats(s["idx_eager_autocast"], s["z_eager"], s["idx_ref"], s["z_ref"], s["margin"])
+    for name, st in (("engine", eng), ("eager_bf16_autocast+fp32_search", ref), ("eager_bf16_autocast_incl_search", ref_ac)):
+        _report("default/" + name, **{k: (round(v, 4) if isinstance(v, float) else v) for k, v in st.items()})
+    assert eng["agree_all"] >= ref["agree_all"] - 0.002
+    assert eng["z_err_rms"] <= ref["z_err_rms"] * 1.05
+    assert eng["max_margin_of_disagreement"] <= max(ref["max_margin_of_disagreement"], EPS_MARGIN)
+    assert eng["disagree_above_eps"] == 0
+
+
+@pytest.mark.parametrize("name", ["tiny", "mid"])
+def test_small_spec_parity_on_4800_frames(name):
+    """The golden files hold 200 frames per spec; the agree_all bar needs a sample where 2.5 % is not 5 frames."""
+    spec = SPECS[name]
+    w = pkg.init_random_weights(spec, seed=0)
+    gen = pkg.B200Generator(spec, w, device="cuda", max_positions=256)
+    oracle = OracleGenerator(spec, w)
+    torch.set_num_threads(os.cpu_count() or 1)
+    wav = torch.stack([pkg.synth_audio(32000, seed=77, file_id=i) for i in range(N_SAMPLE_WINDOWS)])
+    codes, _, z = gen.encode(wav.cuda(), return_margin=True, return_latents=True)
+    with torch.no_grad():
+        z_ref = oracle.encoder(oracle.pad_audio(wav))
+        _, idx_ref, margin = oracle.quantizer.inference(z_ref, return_margin=True)
+    st = _sample_stats(codes.cpu(), z.cpu(), idx_ref, z_ref, margin)
+    _report(name + "/4800", **{k: (round(v, 4) if isinstance(v, float) else v) for k, v in st.items()})
+    assert st["z_err_max"] <= Z_TOL and st["disagree_above_eps"] == 0 and st["agree_all"] >= AGREE_ALL_MIN
 
 
 def test_stream_session_equals_stateless_calls(bundle):

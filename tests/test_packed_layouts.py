@@ -79,3 +79,30 @@ def test_c_abi_library_exports_every_declared_symbol():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             pkg.AudioTokenizer("MagiCodec-50Hz-Base")            # product path must fail loudly without a GPU
+
+
+def test_checkpoint_roundtrip_is_weights_only(tmp_path):
+    """save_checkpoint writes plain containers + tensors; load_checkpoint never unpickles code (weights_only=True)."""
+    import pickle
+
+    import pytest
+    import torch
+
+    import realtime_codec_agent_b200 as pkg
+
+    spec = pkg.TINY_SPEC
+    w = pkg.init_random_weights(spec, seed=3)
+    path = tmp_path / "tiny.pt"
+    pkg.save_checkpoint(str(path), spec, w)
+    spec2, w2 = pkg.load_checkpoint(str(path))
+    assert spec2 == spec and set(w2) == set(w)
+    assert all(torch.equal(w[k], w2[k]) for k in w)
+
+    class Evil:
+        def __reduce__(self):
+            return (print, ("code ran while loading a checkpoint",))
+
+    bad = tmp_path / "evil.pt"
+    torch.save({"spec": {}, "weights": {}, "x": Evil()}, str(bad))
+    with pytest.raises((pickle.UnpicklingError, RuntimeError)):
+        pkg.load_checkpoint(str(bad))
