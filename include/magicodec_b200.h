@@ -103,6 +103,26 @@ int mc_vq_search(mc_handle* h, const float* z, int32_t M, int64_t* codes, float*
 /* Copies the cached projected codebook, fp32 [K, dq]. */
 int mc_codebook(mc_handle* h, float* out, mc_stream_t stream);
 
+/* ---- corpus ingest on the device: what _prep_audio_for_tokenization (audio_tokenizer.py:203-215: int16 -> float,
+ * librosa.to_mono, librosa.resample) and the offline CLI's loader do on the host in the reference.
+ * pcm: DEVICE pointer to interleaved frames [frames][channels] in `format`; out: planar fp32 [C_out, out_ld]
+ * (C_out = 1 when mix_mono: mean over channels like np.mean(axis=0)). */
+enum { MC_PCM_U8 = 0, MC_PCM_S16 = 1, MC_PCM_S24 = 2, MC_PCM_S32 = 3, MC_PCM_F32 = 4, MC_PCM_F64 = 5, MC_PCM_ULAW = 6, MC_PCM_ALAW = 7 };
+int mc_op_pcm_to_f32(mc_handle* h, const void* pcm, int32_t format, int32_t big_endian, int32_t channels, int64_t frames,
+                     int32_t mix_mono, float* out, int64_t out_ld, mc_stream_t stream);
+/* Rational polyphase FIR resampler (scipy.signal.resample_poly semantics: taps already scaled by `up` and left-padded
+ * for alignment, pre_remove = leading outputs dropped): in planar fp32 [C, in_ld] -> out planar fp32 [C, out_ld]. */
+int mc_op_resample(mc_handle* h, const float* in, int64_t in_ld, int32_t channels, int64_t n_in, int32_t up, int32_t down,
+                   const float* taps, int32_t n_taps, int64_t pre_remove, float* out, int64_t out_ld, int64_t n_out,
+                   mc_stream_t stream);
+
+/* Host-side FLAC decoder (no CUDA; libri-light ships as .flac and no audio library is installed offline — the
+ * reference loads it through librosa/soundfile/libFLAC).  data: the whole file in HOST memory.  mc_flac_decode writes
+ * interleaved [frames][channels] PCM: int16 for streams of <= 16 bits per sample (MC_PCM_S16), else int32 left-justified
+ * (MC_PCM_S32); verifies every frame's CRC-8 / CRC-16 and the STREAMINFO sample count. */
+int mc_flac_info(const uint8_t* data, int64_t n, int32_t* sample_rate, int32_t* channels, int32_t* bits, int64_t* total_samples);
+int mc_flac_decode(const uint8_t* data, int64_t n, void* out, int64_t capacity_frames, int64_t* decoded);
+
 /* ---- streaming sessions: the rolling context of tokenize_audio / detokenize_audio
  * (audio_tokenizer.py:72-74, 111-113) resident in HBM; the steady state is one CUDA-graph launch per
  * call.  chunk / codes / outputs are HOST pointers (staged through pinned memory); these calls

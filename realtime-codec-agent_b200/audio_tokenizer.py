@@ -288,9 +288,9 @@ class AudioTokenizer:
 
 
 def _resample(wav: np.ndarray, orig_sr: int, target_sr: int) -> np.ndarray:
-    """Polyphase resampler standing in for ``librosa.resample`` (audio_tokenizer.py:214; librosa's
-    default soxr kernel is not available offline, so sample values differ in the last bits)."""
-    from scipy.signal import resample_poly
+    """Stand-in for ``librosa.resample`` (audio_tokenizer.py:214; default res_type 'soxr_hq'): a linear-phase
+    polyphase FIR designed to soxr-HQ's specification (audio_io.resample_plan).  soxr itself is not available
+    offline, so sample values differ from the reference's in the transition band; INTEGRATION.md states by how much."""
+    from .audio_io import resample
 
-    g = math.gcd(int(orig_sr), int(target_sr))
-    return resample_poly(wav, int(target_sr) // g, int(orig_sr) // g, axis=-1).astype(np.float32)
+    return resample(wav, int(orig_sr), int(target_sr))

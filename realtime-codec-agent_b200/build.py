@@ -24,7 +24,7 @@ def _sources_digest() -> str:
     roots = [CSRC, os.path.join(os.path.dirname(PKG_DIR), "include")]
     for root in roots:
         for name in sorted(os.listdir(root)):
-            if name.endswith((".cu", ".cuh", ".h")):
+            if name.endswith((".cu", ".cuh", ".h", ".cpp")):
                 with open(os.path.join(root, name), "rb") as f:
                     hsh.update(name.encode())
                     hsh.update(f.read())
@@ -49,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-Xcompiler", "-fPIC,-O2,-Wall", "-shared",
         "-Xptxas", "-v" if verbose else "-O3",
-        "-o", LIB_PATH, os.path.join(CSRC, "engine.cu"),
+        "-o", LIB_PATH, os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "audio_decode.cpp"),
         "-lcudart",
     ]
     proc = subprocess.run(cmd, capture_output=True, text=True)

@@ -165,6 +165,7 @@ class ManifestEntry:
     n_windows: int
     crc32: int
     rank: int
+    path: str = ""          # file path relative to --audio_path, without extension (the CLI fills it in)
 
 
 def manifest_entry(file_id: int, channel: int, codes: torch.Tensor, n_windows: int, rank: int) -> ManifestEntry:
@@ -172,9 +173,9 @@ def manifest_entry(file_id: int, channel: int, codes: torch.Tensor, n_windows: i
     return ManifestEntry(file_id, channel, int(codes.numel()), n_windows, zlib.crc32(raw) & 0xFFFFFFFF, rank)
 
 
-def gather_manifests(local: List[ManifestEntry], device: Optional[torch.device] = None) -> List[ManifestEntry]:
-    """all_gather of per-rank manifests: lengths first, then zero-padded byte buffers (two small
-    collectives per corpus run; no collective touches the data path)."""
+def gather_objects(local: list, device: Optional[torch.device] = None) -> list:
+    """all_gather of one JSON-serialisable list per rank, concatenated in rank order: lengths first, then zero-padded
+    byte buffers (two small collectives; NCCL over NVLink on GPUs, gloo in the CPU tests)."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
@@ -182,19 +183,27 @@ def gather_manifests(local: List[ManifestEntry], device: Optional[torch.device] 
     world = dist.get_world_size()
     backend = dist.get_backend()
     dev = device if (device is not None and backend == "nccl") else torch.device("cpu")
-    payload = json.dumps([asdict(e) for e in local]).encode()
+    payload = json.dumps(local).encode()
     n = torch.tensor([len(payload)], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n)
-    cap = int(max(int(s.item()) for s in sizes))
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(sizes, n)
+    sizes = sizes.cpu().tolist()                                   # one D2H for all ranks' lengths
+    cap = max(1, int(max(sizes)))
     buf = torch.zeros(cap, dtype=torch.uint8, device=dev)
-    buf[: len(payload)] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
-    bufs = [torch.zeros_like(buf) for _ in range(world)]
-    dist.all_gather(bufs, buf)
-    merged: List[ManifestEntry] = []
-    for s, b in zip(sizes, bufs):
-        raw = bytes(b[: int(s.item())].cpu().numpy().tobytes())
-        merged.extend(ManifestEntry(**d) for d in json.loads(raw.decode()))
+    if payload:
+        buf[: len(payload)] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+    bufs = torch.zeros(world * cap, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(bufs, buf)
+    host = bufs.cpu().numpy().reshape(world, cap)
+    merged = []
+    for r in range(world):
+        merged.extend(json.loads(host[r, : int(sizes[r])].tobytes().decode()))
+    return merged
+
+
+def gather_manifests(local: List[ManifestEntry], device: Optional[torch.device] = None) -> List[ManifestEntry]:
+    """all_gather of per-rank manifests (two small collectives per corpus run; no collective touches the data path)."""
+    merged = [ManifestEntry(**d) for d in gather_objects([asdict(e) for e in local], device)]
     merged.sort(key=lambda e: (e.file_id, e.channel))
     return merged
 

@@ -6,6 +6,7 @@
 #include "attn_vq_simt.cuh"
 #include "elementwise.cuh"
 #include "gemm_sm100.cuh"
+#include "ingest.cuh"
 #include "post_sm100.cuh"
 #include "vq_sm100.cuh"
 
@@ -722,6 +723,35 @@ int mc_op_emit_chunk(mc_handle* h, const float* wav, int32_t n_have, int32_t chu
   emit_chunk_kernel<<<1, POST_THREADS, 0, (cudaStream_t)stream>>>(wav, n_have, chunk, fade, has_prev, target_rms,
                                                                   silence_rms_threshold, fade_in, prev_tail, out);
   MC_LAUNCH_CHECK(h, "emit_chunk_kernel");
+  return MC_OK;
+}
+
+int mc_op_pcm_to_f32(mc_handle* h, const void* pcm, int32_t format, int32_t big_endian, int32_t channels, int64_t frames,
+                     int32_t mix_mono, float* out, int64_t out_ld, mc_stream_t stream) {
+  MC_ENTER(h);
+  if (!pcm || !out || channels < 1 || frames < 1 || format < PCM_U8 || format > PCM_ALAW || (!mix_mono && out_ld < frames))
+    return h->fail(MC_ERR_ARG, "mc_op_pcm_to_f32: bad arguments (format %d, channels %d, frames %lld)", format, channels, (long long)frames);
+  if ((format == PCM_F32 && (reinterpret_cast<uintptr_t>(pcm) & 3)) || (format == PCM_F64 && (reinterpret_cast<uintptr_t>(pcm) & 7)))
+    return h->fail(MC_ERR_ARG, "mc_op_pcm_to_f32: float payload is not naturally aligned");
+  McProfScope prof(h, 3, 0.0, (double)frames * channels * 2.0 + (double)frames * (mix_mono ? 1 : channels) * 4.0, (cudaStream_t)stream);
+  pcm_to_f32_kernel<<<ew_grid(h, frames, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const unsigned char*>(pcm), format, big_endian, channels, (long long)frames, mix_mono, out, (long long)out_ld);
+  MC_LAUNCH_CHECK(h, "pcm_to_f32_kernel");
+  return MC_OK;
+}
+
+int mc_op_resample(mc_handle* h, const float* in, int64_t in_ld, int32_t channels, int64_t n_in, int32_t up, int32_t down,
+                   const float* taps, int32_t n_taps, int64_t pre_remove, float* out, int64_t out_ld, int64_t n_out,
+                   mc_stream_t stream) {
+  MC_ENTER(h);
+  if (!in || !taps || !out || channels < 1 || n_in < 1 || n_out < 1 || up < 1 || down < 1 || n_taps < 1 || pre_remove < 0 ||
+      in_ld < n_in || out_ld < n_out)
+    return h->fail(MC_ERR_ARG, "mc_op_resample: bad arguments (up %d, down %d, taps %d)", up, down, n_taps);
+  McProfScope prof(h, 3, 2.0 * channels * (double)n_out * ((double)n_taps / up), (double)channels * (n_in + n_out) * 4.0, (cudaStream_t)stream);
+  resample_poly_kernel<<<ew_grid(h, (long long)channels * n_out, 256), 256, 0, (cudaStream_t)stream>>>(
+      in, (long long)in_ld, channels, (long long)n_in, up, down, taps, n_taps, (long long)pre_remove, out, (long long)out_ld,
+      (long long)n_out);
+  MC_LAUNCH_CHECK(h, "resample_poly_kernel");
   return MC_OK;
 }
 

@@ -25,3 +25,30 @@ class OracleBackedGen:
             z = self.oracle.encoder(self.oracle.pad_audio(wav.float()))
             idx = self.oracle.quantizer.inference(z)[1]
         return idx[:, -keep_last_frames:] if keep_last_frames > 0 else idx
+
+
+class HostIngest:
+    """The corpus pipeline's staging interface (audio_io.DeviceIngest) for the CPU tests: numpy / scipy mirrors of
+    the ingest kernels around the oracle-backed model.  Test infrastructure only."""
+
+    def __init__(self, gen):
+        self.gen = gen
+
+    def host_buffer(self, nbytes):
+        return torch.empty(nbytes, dtype=torch.uint8)
+
+    def upload(self, pcm, host_tensor=None):
+        return pcm
+
+    def wait_uploaded(self, staged):
+        pass
+
+    def convert(self, pcm, staged, mono):
+        from realtime_codec_agent_b200 import audio_io
+        x = audio_io.pcm_to_float(pcm, mono=mono)
+        if pcm.sample_rate != self.gen.sample_rate:
+            x = audio_io.resample(x, pcm.sample_rate, self.gen.sample_rate)
+        return torch.from_numpy(x.copy())
+
+    def codes_to_host(self, codes):
+        return [c.clone() for c in codes], (lambda: None)

@@ -173,7 +173,7 @@ def test_inputs_longer_than_the_rope_table_grow_it():
     again = [sess.push_audio(w[None, i * 1600:(i + 1) * 1600], 5).copy() for i in range(25)]     # replays re-captured graphs
     assert all(np.array_equal(a, b) for a, b in zip(first, again))
     tok = pkg.AudioTokenizer(codec_model=g, device="cuda")
-    s = tok.tokenize_audio(w[: 16000 * 45])                                # 45 s one-shot: 2250 frames
+    s = tok.tokenize_audio(pkg.synth_audio(16000 * 45, file_id=2).numpy())  # 45 s one-shot: 2250 frames
     assert len(s) == 2250 and g.max_positions == 4096
     (_, out), _, _ = tok.detokenize_audio(s)
     assert out.shape == (16000 * 45,)
