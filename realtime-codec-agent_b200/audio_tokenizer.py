@@ -112,7 +112,41 @@ class AudioTokenizer:
         sr, wav = (self.sampling_rate, audio) if isinstance(audio, np.ndarray) else audio
         step = int(chunk_size_secs * sr)
         total = wav.shape[-1]
-        return "".join(self.tokenize_audio((sr, wav[..., s:s + step])) for s in range(0, total, step))
+        with self._lock:
+            fast = self._chunked_tokenize_batched(sr, wav, step, chunk_size_secs) if self._native else None
+            if fast is not None:
+                return fast
+            return "".join(self.tokenize_audio((sr, wav[..., s:s + step])) for s in range(0, total, step))
+
+    @torch.inference_mode()
+    def _chunked_tokenize_batched(self, sr: int, wav: np.ndarray, step: int, chunk_size_secs: float) -> Optional[str]:
+        """The loop above as ONE batched corpus encode (corpus.encode_streams: every chunk's 2.0 s window in a few
+        launches) — the same kernels, hence the same codes, as the offline training-data encode, which is what the
+        agent wants for its enrolment prompt (realtime_agent_v2.py:77).  Taken only where it is provably the loop's
+        result: empty context, no per-chunk resampling, and chunk sizes for which the per-chunk character count
+        int(secs * framerate * C) is a whole number of frames.  Leaves the contexts as the loop would."""
+        from . import corpus
+        C = self.num_channels
+        if self.tokenize_context.shape[-1] != 0 or sr != self.sampling_rate or step <= 0 or wav.shape[-1] == 0:
+            return None
+        full = self._prep_audio_for_tokenization((sr, wav)).reshape(C, -1)
+        total = full.shape[-1]
+        per_chunk = int(step / self.sampling_rate * self.framerate)
+        if int(step / self.sampling_rate * self.framerate * C) != C * per_chunk or per_chunk <= 0:
+            return None
+        if C > 1 and total % step != 0:
+            return None                                    # a ragged tail can cut a frame in two across channels (:99-101)
+        gen = self.codec_model
+        dev = torch.from_numpy(np.ascontiguousarray(full)).to(self.device)
+        codes = corpus.encode_streams(gen, [dev[c] for c in range(C)], chunk_size_secs, self.context_secs)
+        per_channel = torch.stack(codes).cpu().numpy()[:, None, :]             # [C,1,F]
+        text = self._interleave_chars(per_channel)
+        last_new = total - ((total - 1) // step) * step
+        keep = max(last_new, self.context_samples)
+        self.tokenize_context = full[..., -keep:].astype(np.float32, copy=True)
+        self._stream_session().load_audio(self.tokenize_context[..., -self.context_samples:])
+        self._session_audio_ok = True
+        return text
 
     def tokenize_audio(self, audio: AudioLike) -> str:
         with self._lock:

@@ -6,6 +6,7 @@
 #include "attn_vq_simt.cuh"
 #include "elementwise.cuh"
 #include "gemm_sm100.cuh"
+#include "gemm_splitk_sm100.cuh"
 #include "ingest.cuh"
 #include "post_sm100.cuh"
 #include "vq_sm100.cuh"
@@ -105,6 +106,64 @@ int launch_gemm_pair(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   return launch_gemm_pair_epi<EPI_GENERIC>(h, p, ma, mb, mo, pairs, stream);
 }
 
+// Few-rows GEMM with K split over a cluster (gemm_splitk_sm100.cuh): S CTAs per 128 x 64 output tile.
+template <int S>
+int launch_gemm_splitk_s(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
+  constexpr int BN = 64;
+  const CUtensorMap *ma, *mb;
+  MC_TRY(get_map_2d_bf16(h, c.A, (uint64_t)c.a_k_wrap, (uint64_t)c.a_rows, GEMM_BK, GEMM_BM, &ma));
+  MC_TRY(get_map_2d_bf16(h, c.W, (uint64_t)c.K, (uint64_t)c.N, GEMM_BK, BN, &mb));
+  GemmParams p;
+  p.tma_store = 0;
+  p.M = c.M; p.N = c.N; p.K = c.K; p.a_k_wrap = c.a_k_wrap;
+  p.bias = c.bias; p.act = c.act; p.out_mode = c.out_mode; p.out = c.out; p.ldo = c.ldo;
+  p.grp_in = c.grp_in; p.grp_valid = c.grp_valid; p.grp_stride = c.grp_stride; p.grp_off = c.grp_off;
+  p.rope_cols = c.rope_cols; p.rope_period = c.rope_period; p.rope_offset = c.rope_offset;
+  p.rope_ld = h->spec.max_positions;
+  p.rope_cos = c.rope_period > 0 ? h->ptr<float>("rope.cos") : nullptr;
+  p.rope_sin = c.rope_period > 0 ? h->ptr<float>("rope.sin") : nullptr;
+  auto kernel = gemm_splitk_sm100_kernel<BN, S>;
+  MC_TRY(mc_allow_smem(h, kernel, GemmSkCfg<BN>::kSmemBytes));
+  const int m_tiles = (c.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (c.N + BN - 1) / BN;
+  const double valid_rows = c.grp_in == INT_MAX ? (double)c.M : (double)c.M / c.grp_in * c.grp_valid;
+  const double out_bytes = valid_rows * c.N * (c.out_mode == OUT_BF16 ? 2.0 : (c.out_mode == OUT_F32 ? 4.0 : 8.0));
+  McProfScope prof(h, 0, 2.0 * valid_rows * c.N * c.K, valid_rows * c.a_k_wrap * 2.0 + (double)c.N * c.K * 2.0 + out_bytes, stream);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(m_tiles * n_tiles * S); cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = GemmSkCfg<BN>::kSmemBytes; cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = h->pdl ? 2 : 1;
+  (void)cudaLaunchKernelEx(&cfg, kernel, *ma, *mb, p);
+  MC_LAUNCH_CHECK(h, "gemm_splitk_sm100_kernel");
+  return MC_OK;
+}
+
+// S for a few-rows GEMM, or 0: the largest split (<= 8) that divides the k-blocks and keeps the grid within two CTAs per SM
+int pick_split_k(const mc_handle* h, const GemmCall& c) {
+  if (c.M > 2 * GEMM_BM) return 0;
+  const int base = ((c.M + GEMM_BM - 1) / GEMM_BM) * ((c.N + 63) / 64);
+  const int num_kb = c.K / GEMM_BK;
+  for (int s = 8; s >= 2; s >>= 1)
+    if (num_kb % s == 0 && base * s <= 2 * h->num_sms) return s;
+  return 0;
+}
+
+int launch_gemm_splitk(mc_handle* h, const GemmCall& c, int S, cudaStream_t stream) {
+  if (c.rope_period > 0 && c.rope_cols % 64 != 0) return h->fail(MC_ERR_ARG, "split-K gemm: rope needs 64-wide heads");
+  if ((c.K / GEMM_BK) % S != 0) return h->fail(MC_ERR_ARG, "split-K gemm: %d k-blocks do not split %d ways", c.K / GEMM_BK, S);
+  switch (S) {
+    case 2: return launch_gemm_splitk_s<2>(h, c, stream);
+    case 4: return launch_gemm_splitk_s<4>(h, c, stream);
+    case 8: return launch_gemm_splitk_s<8>(h, c, stream);
+    default: return h->fail(MC_ERR_ARG, "split-K gemm: unsupported split %d", S);
+  }
+}
+
 int launch_gemm(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   if (c.K % GEMM_BK != 0 || c.K % c.a_k_wrap != 0 || c.a_k_wrap % GEMM_BK != 0)
     return h->fail(MC_ERR_ARG, "gemm: K=%d a_k_wrap=%d must be multiples of %d", c.K, c.a_k_wrap, GEMM_BK);
@@ -112,6 +171,11 @@ int launch_gemm(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   if (c.rope_period > 0 && c.rope_period + c.rope_offset > h->spec.max_positions)
     return h->fail(MC_ERR_ARG, "gemm: rope period %d exceeds table rows %d", c.rope_period, h->spec.max_positions);
   int bn = c.block_n;
+  if (bn >= 1002 && bn <= 1008) return launch_gemm_splitk(h, c, bn - 1000, stream);   // forced (tests / A-B timing)
+  if (bn == 0 && (h->split_k == 2 || (h->split_k == 1 && h->in_session))) {
+    const int S = pick_split_k(h, c);
+    if (S >= 2) return launch_gemm_splitk(h, c, S, stream);
+  }
   {
     // CTA pairs whenever there is at least one 256 x 256 tile per pair of SMs
     const int m2 = (c.M + 255) / 256, n2 = (c.N + 255) / 256;
@@ -789,6 +853,11 @@ int mc_set_option(mc_handle* h, const char* key, int32_t value) {
   else if (k == "fast_epilogue") h->fast_epilogue = value != 0;
   else if (k == "pdl") h->pdl = value != 0;
   else if (k == "attn_p_tmem") h->attn_p_tmem = value != 0;
+  else if (k == "small_m_split_k") {   // 0 never, 1 streaming sessions only (default), 2 every GEMM of <= 256 rows
+    if (value < 0 || value > 2) return h->fail(MC_ERR_ARG, "mc_set_option: small_m_split_k is 0, 1 or 2");
+    h->split_k = value;
+    h->tensor_gen++;                   // sessions re-capture their graphs with the other kernels
+  }
   else if (k == "max_positions") {   // rows of the re-registered rope.cos / rope.sin tables (B200Generator grows them on demand)
     if (value < 1) return h->fail(MC_ERR_ARG, "mc_set_option: max_positions must be positive");
     h->spec.max_positions = value;
@@ -889,7 +958,19 @@ void stream_drop_graphs(mc_stream* s) {
 // Runs `body` directly the first time a key is seen (that run sizes the workspace and fills the TMA
 // descriptor cache), captures it into a graph the second time, and replays the graph afterwards.
 template <typename Body>
+int run_or_replay_impl(mc_stream* s, std::tuple<int, int, int, int, int> key, cudaStream_t stream, Body body);
+
+// Everything a session launches (directly or while capturing) is "in session": few-rows GEMMs take the split-K kernels.
+template <typename Body>
 int run_or_replay(mc_stream* s, std::tuple<int, int, int, int, int> key, cudaStream_t stream, Body body) {
+  s->h->in_session = true;
+  const int rc = run_or_replay_impl(s, key, stream, body);
+  s->h->in_session = false;
+  return rc;
+}
+
+template <typename Body>
+int run_or_replay_impl(mc_stream* s, std::tuple<int, int, int, int, int> key, cudaStream_t stream, Body body) {
   mc_handle* h = s->h;
   if (!s->use_graphs || h->profiling) return body();
   auto& e = s->graphs[key];

@@ -64,6 +64,10 @@ struct mc_handle {
   int gemm_pair = 1;  // use the cta_group::2 GEMM where the shape allows
   bool fast_epilogue = true;  // mode-specialised, software-pipelined epilogues in the CTA-pair GEMM
   bool attn_p_tmem = true;    // attention: P through tensor memory (v4) instead of shared memory (v3)
+  // GEMMs of <= 256 rows with K split over a thread-block cluster (gemm_splitk_sm100.cuh): 0 never, 1 inside streaming
+  // sessions (the latency path; stateless mc_encode / mc_decode stay batch-invariant), 2 always
+  int split_k = 1;
+  bool in_session = false;
   bool pdl = true;            // programmatic dependent launch between consecutive kernels of a pass
   bool shared_stem = true;  // overlapping hop-aligned windows share one pass of the conv stack (exact)
   // optional per-class device timing (bench.py's roofline): event pairs around each launch

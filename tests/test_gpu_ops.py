@@ -156,6 +156,74 @@ def test_gemm_rowblock_conv_view_and_group_remap(gen):
     assert torch.all(out[:, :pad_next] == 7.0)                       # padding rows untouched
 
 
+@pytest.mark.parametrize("S", [2, 4, 8])
+@pytest.mark.parametrize("M,N,K", [(1, 1024, 1024), (77, 512, 512), (100, 3072, 1024), (100, 1024, 4096), (128, 16, 1024),
+                                   (200, 1024, 1024), (256, 4096, 1024), (100, 72, 512)])
+def test_splitk_gemm_every_epilogue(gen, S, M, N, K):
+    """gemm_splitk_sm100_kernel (K split over a cluster of S CTAs, fixed-order DSMEM reduction): fp32 / bf16+GELU /
+    residual / RoPE epilogues against fp32 torch, and bit-reproducible run to run."""
+    A = _rand((M, K), seed=41).to(torch.bfloat16)
+    W = (_rand((N, K), seed=42) / math.sqrt(K)).to(torch.bfloat16)
+    bias = _rand((N,), seed=43)
+    ref = A.float() @ W.float().t() + bias
+    bn = 1000 + S
+    out = gen.op_gemm(A, W, bias=bias, out_mode=1, block_n=bn)
+    assert (out - ref).abs().max().item() < 2e-3
+    assert torch.equal(out, gen.op_gemm(A, W, bias=bias, out_mode=1, block_n=bn))
+    nob = gen.op_gemm(A, W, out_mode=1, block_n=bn)
+    assert (nob - (ref - bias)).abs().max().item() < 2e-3
+    act = gen.op_gemm(A, W, bias=bias, act=1, out_mode=0, block_n=bn)
+    assert act.dtype == torch.bfloat16 and (act.float() - gelu_tanh(ref)).abs().max().item() < 0.03
+    x0 = _rand((M, N), seed=44)
+    x = x0.clone()
+    gen.op_gemm(A, W, bias=bias, out_mode=2, out=x, block_n=bn)
+    assert (x - (x0 + ref)).abs().max().item() < 2e-3
+    # against the single-accumulator kernel: same products, different fp32 summation order
+    one = gen.op_gemm(A, W, bias=bias, out_mode=1, block_n=64)
+    assert (out - one).abs().max().item() < 1e-4
+    if N % 128 == 0:
+        Fr = 50 if M % 50 == 0 else M
+        r1 = gen.op_gemm(A, W, bias=bias, out_mode=1, rope_cols=N // 2, rope_period=Fr, block_n=bn)
+        r0 = gen.op_gemm(A, W, bias=bias, out_mode=1, rope_cols=N // 2, rope_period=Fr, block_n=64)
+        assert (r1 - r0).abs().max().item() < 1e-4
+        rb = gen.op_gemm(A, W, bias=bias, out_mode=0, rope_cols=N // 2, rope_period=Fr, block_n=bn)
+        assert (rb.float() - r0).abs().max().item() < 0.03
+
+
+def test_splitk_gemm_conv_view_and_auto_selection(gen):
+    """Row-block (implicit conv) A view + group remap through the split-K kernel, and the automatic choice: GEMMs of
+    <= 256 rows take it unless small_m_split_k is switched off (then they equal the 128 x 64 single-CTA kernel bit for bit)."""
+    Bn, Tout, blk, N, pad_next = 2, 100, 128, 256, 4
+    rows = Bn * (1 + Tout)
+    buf = _rand((rows, blk), seed=45).to(torch.bfloat16)
+    W = (_rand((N, 2 * blk), seed=46) / 16).to(torch.bfloat16)
+    bias = _rand((N,), seed=47)
+    flat = torch.cat([buf.reshape(-1), torch.zeros(blk, device="cuda", dtype=torch.bfloat16)])
+    idx = torch.arange(rows, device="cuda")[:, None] * blk + torch.arange(2 * blk, device="cuda")[None, :]
+    ref = gelu_tanh(flat[idx].float() @ W.float().t() + bias).view(Bn, 1 + Tout, N)[:, :Tout]
+    for bn in (1002, 1004):
+        out = torch.full((Bn, pad_next + Tout, N), 7.0, device="cuda", dtype=torch.bfloat16)
+        gen.op_gemm(buf, W, bias=bias, act=1, out_mode=0, out=out, a_k_wrap=blk, M=rows, K=2 * blk, grp_in=1 + Tout,
+                    grp_valid=Tout, grp_stride=(pad_next + Tout) * N, grp_off=pad_next * N, ldo=N, block_n=bn)
+        assert (out[:, pad_next:].float() - ref).abs().max().item() < 0.03
+        assert torch.all(out[:, :pad_next] == 7.0)
+    A = _rand((100, 1024), seed=48).to(torch.bfloat16)
+    Wl = (_rand((1024, 1024), seed=49) / 32).to(torch.bfloat16)
+    big = _rand((300, 1024), seed=50).to(torch.bfloat16)
+    single = gen.op_gemm(A, Wl, out_mode=1, block_n=64)
+    assert torch.equal(gen.op_gemm(A, Wl, out_mode=1), single)                 # stateless calls: batch-invariant kernels by default
+    try:
+        gen.set_option("small_m_split_k", 2)                                   # every GEMM of <= 256 rows
+        auto = gen.op_gemm(A, Wl, out_mode=1)
+        assert torch.equal(auto, gen.op_gemm(A, Wl, out_mode=1, block_n=1008))  # 16 n-tiles x 8 splits = 128 CTAs
+        assert not torch.equal(auto, single) and (auto - single).abs().max().item() < 1e-4
+        assert torch.equal(gen.op_gemm(big, Wl, out_mode=1), gen.op_gemm(big, Wl, out_mode=1, block_n=64))   # > 256 rows: never
+        gen.set_option("small_m_split_k", 0)
+        assert torch.equal(gen.op_gemm(A, Wl, out_mode=1), single)
+    finally:
+        gen.set_option("small_m_split_k", 1)
+
+
 def test_rmsnorm(gen):
     x = _rand((333, 512), scale=3.0, seed=16)
     g = 1.0 + 0.1 * _rand((512,), seed=17)

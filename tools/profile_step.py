@@ -41,7 +41,9 @@ def run(tag, iters=3):
 
 codes = run("default")
 if only_default:
-    run("default")
+    torch.cuda.profiler.start()          # ncu --profile-from-start off captures one warm batch
+    run("default", iters=1)
+    torch.cuda.profiler.stop()
 else:
     gen.set_debug_impl(attention=3)
     c2 = run("attention v2 (no staged loads)")
