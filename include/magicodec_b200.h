@@ -145,6 +145,24 @@ int mc_stream_push_codes(mc_stream* s, const int64_t* codes, int32_t n, int32_t 
                          int32_t* samples_out, mc_stream_t stream);
 int mc_stream_set_graphs(mc_stream* s, int32_t enabled); /* 0: direct launches (A/B timing, debugging) */
 
+/* ---- session pool: many independent rolling contexts batched per call.  tts_server.py:59,158
+ * tokenizes every active stream chunk by chunk on one shared tokenizer, realtime_agent_resources.py:41-49 runs two
+ * agents on one model; alone, each session is a batch-1 pass that streams every weight for 100 rows.  Sessions whose
+ * contexts have the same length are pushed together as ONE B = n*channels launch.  Per session the semantics are those
+ * of mc_stream_push_audio / mc_stream_push_codes.  slots: n distinct indices < max_sessions; chunks HOST fp32
+ * [n][C][len] -> codes_out HOST int64 [n][C][keep]; codes HOST int64 [n][C][len] -> wav_out HOST fp32 [n][C][keep]. */
+typedef struct mc_pool mc_pool;
+int mc_pool_create(mc_handle* h, int32_t channels, int32_t context_samples, int32_t max_chunk_samples, int32_t max_sessions,
+                   mc_pool** out);
+int mc_pool_destroy(mc_pool* p);
+int mc_pool_reset(mc_pool* p, int32_t slot, int32_t audio, int32_t codes);
+int mc_pool_context_len(mc_pool* p, int32_t slot, int32_t* audio_len, int32_t* code_len);
+int mc_pool_set_graphs(mc_pool* p, int32_t enabled);
+int mc_pool_push_audio(mc_pool* p, const int32_t* slots, int32_t n, const float* chunks, int32_t len, int32_t keep_frames,
+                       int64_t* codes_out, int32_t* frames_out, mc_stream_t stream);
+int mc_pool_push_codes(mc_pool* p, const int32_t* slots, int32_t n, const int64_t* codes, int32_t len, int32_t keep_samples,
+                       float* wav_out, int32_t* samples_out, mc_stream_t stream);
+
 /* ---- post-decode emit chain of the agent loop (mono sessions), fused behind the decoder in the same
  * CUDA graph: detokenize_audio(codes, preroll = fade) -> pad_or_trim -> normalize_audio_rms (skipped when
  * target_rms <= 0) -> smooth_join with the previous chunk -> the chunk to emit.

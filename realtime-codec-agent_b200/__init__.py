@@ -12,6 +12,8 @@ Public surface (mirrors the reference's interface for this path):
     smooth_join / create_crossfade_ramps / pad_or_trim / normalize_audio_rms   — utils/audio_utils.py:4-46
     OutputChunkEmitter        — RealtimeAgent.detokenize_output_chunk, realtime_agent_v2.py:556-579
     ExternalTTSDuplexAligner  — external_tts_duplex_aligner.py:6-27
+    SessionBatcher / ThreadedSessionBatcher   — many live streams on one engine (tts_server.py:59,158)
+    audio_io (read_audio / load_audio / resample / DeviceIngest), audio_to_codes (the offline CLI)
 """
 from .spec import MagiCodecSpec, DEFAULT_SPEC, TINY_SPEC, MID_SPEC  # noqa: F401
 from .weights import init_random_weights, param_shapes, save_checkpoint, load_checkpoint  # noqa: F401
@@ -28,6 +30,9 @@ def __getattr__(name):
     if name == "B200Generator":
         from .generator import B200Generator
         return B200Generator
+    if name in ("SessionBatcher", "ThreadedSessionBatcher", "SessionPool"):
+        from . import session_batcher
+        return getattr(session_batcher, name)
     if name == "native":
         from . import _native
         return _native

@@ -61,6 +61,13 @@ SYMBOLS = {
     "mc_stream_set_graphs": (C.c_int, [_P, _I32]),
     "mc_stream_set_emit": (C.c_int, [_P, _I32, _I32, C.c_float, C.c_float, _P]),
     "mc_stream_push_codes_emit": (C.c_int, [_P, _P, _I32, _P, C.POINTER(_I32), _P]),
+    "mc_pool_create": (C.c_int, [_P, _I32, _I32, _I32, _I32, C.POINTER(_P)]),
+    "mc_pool_destroy": (C.c_int, [_P]),
+    "mc_pool_reset": (C.c_int, [_P, _I32, _I32, _I32]),
+    "mc_pool_context_len": (C.c_int, [_P, _I32, C.POINTER(_I32), C.POINTER(_I32)]),
+    "mc_pool_set_graphs": (C.c_int, [_P, _I32]),
+    "mc_pool_push_audio": (C.c_int, [_P, _P, _I32, _P, _I32, _I32, _P, C.POINTER(_I32), _P]),
+    "mc_pool_push_codes": (C.c_int, [_P, _P, _I32, _P, _I32, _I32, _P, C.POINTER(_I32), _P]),
     "mc_embed_distance": (C.c_int, [_P, _P, _I32, _I32, _I64, _P, _P, _P, _P]),
     "mc_op_gemm": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _I64,
                              _I32, _I32, _I64, _I64, _I32, _I32, _I32, _P]),

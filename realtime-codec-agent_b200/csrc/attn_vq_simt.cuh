@@ -179,13 +179,21 @@ __global__ void vq_merge_kernel(const VqPartial* __restrict__ partial, int Mq, i
   if (m >= Mq) return;
   float best = INFINITY, second = INFINITY;
   int bidx = 0;
-  for (int s = 0; s < splits; ++s) {
-    const VqPartial pr = partial[static_cast<long long>(s) * Mq + m];
-    if (pr.best < best) {
-      second = fminf(best, pr.second);
-      best = pr.best; bidx = pr.idx;
-    } else {
-      second = fminf(second, pr.best);
+  // eight independent loads in flight per step (a serial walk costs one L2 round trip per split: 11 us at batch 1)
+  for (int s0 = 0; s0 < splits; s0 += 8) {
+    VqPartial pr[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (s0 + u < splits) pr[u] = partial[static_cast<long long>(s0 + u) * Mq + m];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (s0 + u >= splits) break;
+      if (pr[u].best < best) {
+        second = fminf(best, pr[u].second);
+        best = pr[u].best; bidx = pr[u].idx;
+      } else {
+        second = fminf(second, pr[u].best);
+      }
     }
   }
   codes[m] = bidx;

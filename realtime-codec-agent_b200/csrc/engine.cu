@@ -25,6 +25,8 @@ struct GemmCall {
   int grp_in = INT_MAX, grp_valid = INT_MAX; int64_t grp_stride = 0, grp_off = 0;
   int rope_cols = 0, rope_period = 0, rope_offset = 0;
   int block_n = 0;  // 0 = choose
+  const void* prefetch_ptr = nullptr;   // next GEMM's weights (split-K kernel: L2 prefetch)
+  long long prefetch_bytes = 0;
 };
 
 template <int BN>
@@ -122,6 +124,7 @@ int launch_gemm_splitk_s(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   p.rope_ld = h->spec.max_positions;
   p.rope_cos = c.rope_period > 0 ? h->ptr<float>("rope.cos") : nullptr;
   p.rope_sin = c.rope_period > 0 ? h->ptr<float>("rope.sin") : nullptr;
+  if (h->l2_prefetch) { p.prefetch_ptr = c.prefetch_ptr; p.prefetch_bytes = c.prefetch_bytes; }
   auto kernel = gemm_splitk_sm100_kernel<BN, S>;
   MC_TRY(mc_allow_smem(h, kernel, GemmSkCfg<BN>::kSmemBytes));
   const int m_tiles = (c.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (c.N + BN - 1) / BN;
@@ -274,6 +277,10 @@ int run_layers(mc_handle* h, const char* prefix, int n_layers, const StackBufs& 
   std::vector<int> r_in(n_layers), r_out(n_layers);
   {
     int need = std::max(1, std::min(keep_rows, F));
+    // One 128-row tile (a batch-1 streaming pass): dropping rows saves nothing — every GEMM is one tile either way —
+    // and the row compactions would be three more launches on the latency path.  Per-row results do not depend on
+    // which other rows are computed, so this stays bit-identical.
+    if ((long long)B * F <= GEMM_BM) need = F;
     for (int l = n_layers - 1; l >= 0; --l) {
       r_out[l] = need;
       need = (need >= F) ? F : std::min(F, need + s.window_left);
@@ -300,6 +307,7 @@ int run_layers(mc_handle* h, const char* prefix, int n_layers, const StackBufs& 
     g.A = b.hbuf; g.a_rows = Mi; g.a_k_wrap = d; g.W = h->ptr<bf16>(T("wqkv")); g.bias = h->ptr<float>(T("bqkv"));
     g.M = Mi; g.N = 3 * d; g.K = d; g.act = ACT_NONE; g.out_mode = OUT_BF16; g.out = b.qkv; g.ldo = 3 * d;
     g.rope_cols = 2 * d; g.rope_period = Ri; g.rope_offset = F - Ri;
+    g.prefetch_ptr = h->ptr<bf16>(T("wo")); g.prefetch_bytes = (long long)d * d * 2;
     MC_TRY(launch_gemm(h, g, stream));
     MC_TRY(launch_attention(h, b.qkv, b.att, B, Ri, Ro, h->attn_impl, stream));
     if (Ro < Ri) {
@@ -314,15 +322,21 @@ int run_layers(mc_handle* h, const char* prefix, int n_layers, const StackBufs& 
     GemmCall o{};
     o.A = b.att; o.a_rows = Mo; o.a_k_wrap = d; o.W = h->ptr<bf16>(T("wo")); o.bias = h->ptr<float>(T("bo"));
     o.M = Mo; o.N = d; o.K = d; o.act = ACT_NONE; o.out_mode = OUT_F32_RESIDUAL; o.out = x; o.ldo = d;
+    o.prefetch_ptr = h->ptr<bf16>(T("w1")); o.prefetch_bytes = (long long)f * d * 2;
     MC_TRY(launch_gemm(h, o, stream));
     MC_TRY(launch_rmsnorm(h, x, h->ptr<float>(T("norm2")), b.hbuf, Mo, d, INT_MAX, 0, 0, stream));
     GemmCall u{};
     u.A = b.hbuf; u.a_rows = Mo; u.a_k_wrap = d; u.W = h->ptr<bf16>(T("w1")); u.bias = h->ptr<float>(T("b1"));
     u.M = Mo; u.N = f; u.K = d; u.act = ACT_GELU_TANH; u.out_mode = OUT_BF16; u.out = b.ffn; u.ldo = f;
+    u.prefetch_ptr = h->ptr<bf16>(T("w2")); u.prefetch_bytes = (long long)d * f * 2;
     MC_TRY(launch_gemm(h, u, stream));
     GemmCall w{};
     w.A = b.ffn; w.a_rows = Mo; w.a_k_wrap = f; w.W = h->ptr<bf16>(T("w2")); w.bias = h->ptr<float>(T("b2"));
     w.M = Mo; w.N = d; w.K = f; w.act = ACT_NONE; w.out_mode = OUT_F32_RESIDUAL; w.out = x; w.ldo = d;
+    if (l + 1 < n_layers) {
+      snprintf(name, sizeof(name), "%s.layers.%d.wqkv", prefix, l + 1);
+      w.prefetch_ptr = h->ptr<bf16>(name); w.prefetch_bytes = (long long)3 * d * d * 2;
+    }
     MC_TRY(launch_gemm(h, w, stream));
   }
   if (rows > keep_rows) {  // no layers (or window_left = 0 corner cases): compact at the end
@@ -853,6 +867,7 @@ int mc_set_option(mc_handle* h, const char* key, int32_t value) {
   else if (k == "fast_epilogue") h->fast_epilogue = value != 0;
   else if (k == "pdl") h->pdl = value != 0;
   else if (k == "attn_p_tmem") h->attn_p_tmem = value != 0;
+  else if (k == "l2_prefetch") { h->l2_prefetch = value != 0; h->tensor_gen++; }
   else if (k == "small_m_split_k") {   // 0 never, 1 streaming sessions only (default), 2 every GEMM of <= 256 rows
     if (value < 0 || value > 2) return h->fail(MC_ERR_ARG, "mc_set_option: small_m_split_k is 0, 1 or 2");
     h->split_k = value;
@@ -957,20 +972,20 @@ void stream_drop_graphs(mc_stream* s) {
 
 // Runs `body` directly the first time a key is seen (that run sizes the workspace and fills the TMA
 // descriptor cache), captures it into a graph the second time, and replays the graph afterwards.
-template <typename Body>
-int run_or_replay_impl(mc_stream* s, std::tuple<int, int, int, int, int> key, cudaStream_t stream, Body body);
+template <typename Sess, typename Body>
+int run_or_replay_impl(Sess* s, std::tuple<int, int, int, int, int> key, cudaStream_t stream, Body body);
 
 // Everything a session launches (directly or while capturing) is "in session": few-rows GEMMs take the split-K kernels.
-template <typename Body>
-int run_or_replay(mc_stream* s, std::tuple<int, int, int, int, int> key, cudaStream_t stream, Body body) {
+template <typename Sess, typename Body>
+int run_or_replay(Sess* s, std::tuple<int, int, int, int, int> key, cudaStream_t stream, Body body) {
   s->h->in_session = true;
   const int rc = run_or_replay_impl(s, key, stream, body);
   s->h->in_session = false;
   return rc;
 }
 
-template <typename Body>
-int run_or_replay_impl(mc_stream* s, std::tuple<int, int, int, int, int> key, cudaStream_t stream, Body body) {
+template <typename Sess, typename Body>
+int run_or_replay_impl(Sess* s, std::tuple<int, int, int, int, int> key, cudaStream_t stream, Body body) {
   mc_handle* h = s->h;
   if (!s->use_graphs || h->profiling) return body();
   auto& e = s->graphs[key];
@@ -1272,6 +1287,209 @@ int mc_stream_set_graphs(mc_stream* s, int32_t enabled) {
   if (!s) return MC_ERR_ARG;
   s->use_graphs = enabled != 0;
   if (!enabled) stream_drop_graphs(s);
+  return MC_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================
+// Session pool: S independent rolling contexts, batched per call.  tts_server.py:59 tokenizes every
+// 0.1 s of every active TTS stream and realtime_agent_resources.py:41-49 runs two agents on one model: each such
+// session alone is a batch-1 pass that streams all weights for 100 rows.  Sessions whose contexts have the same
+// length are pushed together as ONE B = n*C launch (the Python SessionBatcher groups them), so n sessions cost about
+// one.  Semantics per session are exactly mc_stream_push_audio / mc_stream_push_codes.
+// =====================================================================================
+struct mc_pool {
+  mc_handle* h = nullptr;
+  int C = 1, max_sessions = 0;
+  int ctx_samples = 0, ctx_frames = 0, cap_samples = 0, cap_frames = 0;
+  float* audio[2] = {nullptr, nullptr};        // [max_sessions][C][cap_samples]
+  int64_t* codes[2] = {nullptr, nullptr};      // [max_sessions][C][cap_frames]
+  std::vector<int> audio_len, code_len, acur, ccur;
+  float *pin_chunk = nullptr, *dev_chunk = nullptr, *batch_audio = nullptr;          // [max_sessions*C][cap_samples]
+  int64_t *pin_codes_in = nullptr, *dev_codes_in = nullptr, *batch_codes = nullptr;  // [max_sessions*C][cap_frames]
+  int32_t *pin_table = nullptr, *dev_table = nullptr;                                // [max_sessions][2]
+  int64_t *dev_codes_out = nullptr, *pin_codes_out = nullptr;
+  float *dev_wav_out = nullptr, *pin_wav_out = nullptr;
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int uses = 0; size_t arena_gen = 0; };
+  std::map<std::tuple<int, int, int, int, int>, GraphEntry> graphs;   // (kind, len_before, n_new, keep, batch items)
+  bool use_graphs = true;
+  cudaStream_t own = nullptr;
+  cudaEvent_t order_ev = nullptr;
+};
+
+namespace {
+int pool_check_slots(mc_pool* p, const int32_t* slots, int n, const std::vector<int>& lens, int* common_len, const char* what) {
+  mc_handle* h = p->h;
+  if (!slots || n < 1 || n > p->max_sessions) return h->fail(MC_ERR_ARG, "%s: need 1..%d sessions, got %d", what, p->max_sessions, n);
+  for (int j = 0; j < n; ++j) {
+    if (slots[j] < 0 || slots[j] >= p->max_sessions) return h->fail(MC_ERR_ARG, "%s: slot %d out of range", what, slots[j]);
+    for (int k = 0; k < j; ++k)
+      if (slots[k] == slots[j]) return h->fail(MC_ERR_ARG, "%s: slot %d listed twice", what, slots[j]);
+    if (lens[slots[j]] != lens[slots[0]])
+      return h->fail(MC_ERR_ARG, "%s: sessions %d and %d hold contexts of different length (%d vs %d); batch them separately", what,
+                     slots[0], slots[j], lens[slots[0]], lens[slots[j]]);
+  }
+  *common_len = lens[slots[0]];
+  return MC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int mc_pool_destroy(mc_pool* p) {
+  if (!p) return MC_OK;
+  for (auto& kv : p->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  for (int i = 0; i < 2; ++i) { if (p->audio[i]) cudaFree(p->audio[i]); if (p->codes[i]) cudaFree(p->codes[i]); }
+  for (void* d : {(void*)p->dev_chunk, (void*)p->batch_audio, (void*)p->dev_codes_in, (void*)p->batch_codes, (void*)p->dev_table,
+                  (void*)p->dev_codes_out, (void*)p->dev_wav_out})
+    if (d) cudaFree(d);
+  for (void* q : {(void*)p->pin_chunk, (void*)p->pin_codes_in, (void*)p->pin_table, (void*)p->pin_codes_out, (void*)p->pin_wav_out})
+    if (q) cudaFreeHost(q);
+  if (p->order_ev) cudaEventDestroy(p->order_ev);
+  if (p->own) cudaStreamDestroy(p->own);
+  delete p;
+  return MC_OK;
+}
+
+int mc_pool_create(mc_handle* h, int32_t channels, int32_t context_samples, int32_t max_chunk_samples, int32_t max_sessions,
+                   mc_pool** out) {
+  MC_ENTER(h);
+  if (!out || channels < 1 || context_samples < 1 || max_sessions < 1) return h->fail(MC_ERR_ARG, "mc_pool_create: bad arguments");
+  int hop = 1;
+  for (int i = 0; i < h->spec.n_convs; ++i) hop *= h->spec.conv_strides[i];
+  mc_pool* p = new mc_pool();
+  p->h = h; p->C = channels; p->max_sessions = max_sessions;
+  p->ctx_samples = context_samples;
+  p->ctx_frames = context_samples / hop;
+  p->cap_samples = std::max(context_samples, max_chunk_samples);
+  p->cap_frames = (p->cap_samples + hop - 1) / hop;
+  if (p->cap_frames > h->spec.max_positions) { delete p; return h->fail(MC_ERR_ARG, "mc_pool_create: context exceeds RoPE table"); }
+  p->audio_len.assign(max_sessions, 0); p->code_len.assign(max_sessions, 0);
+  p->acur.assign(max_sessions, 0); p->ccur.assign(max_sessions, 0);
+  const size_t rows = (size_t)max_sessions * channels;
+  const size_t ab = rows * p->cap_samples * 4, cb = rows * p->cap_frames * 8;
+  cudaError_t e = cudaSuccess;
+  auto dev = [&](void** q, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(q, bytes); };
+  auto pin = [&](void** q, size_t bytes) { if (e == cudaSuccess) e = cudaMallocHost(q, bytes); };
+  for (int i = 0; i < 2; ++i) { dev((void**)&p->audio[i], ab); dev((void**)&p->codes[i], cb); }
+  dev((void**)&p->dev_chunk, ab); dev((void**)&p->batch_audio, ab); dev((void**)&p->dev_wav_out, ab);
+  dev((void**)&p->dev_codes_in, cb); dev((void**)&p->batch_codes, cb); dev((void**)&p->dev_codes_out, cb);
+  dev((void**)&p->dev_table, (size_t)max_sessions * 8);
+  pin((void**)&p->pin_chunk, ab); pin((void**)&p->pin_wav_out, ab);
+  pin((void**)&p->pin_codes_in, cb); pin((void**)&p->pin_codes_out, cb);
+  pin((void**)&p->pin_table, (size_t)max_sessions * 8);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->own, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->order_ev, cudaEventDisableTiming);
+  if (e != cudaSuccess) { mc_pool_destroy(p); return h->fail(MC_ERR_NOMEM, "mc_pool_create: %s", cudaGetErrorString(e)); }
+  *out = p;
+  return MC_OK;
+}
+
+int mc_pool_reset(mc_pool* p, int32_t slot, int32_t audio, int32_t codes) {
+  if (!p || slot < 0 || slot >= p->max_sessions) return MC_ERR_ARG;
+  if (audio) p->audio_len[slot] = 0;
+  if (codes) p->code_len[slot] = 0;
+  return MC_OK;
+}
+
+int mc_pool_context_len(mc_pool* p, int32_t slot, int32_t* audio_len, int32_t* code_len) {
+  if (!p || slot < 0 || slot >= p->max_sessions) return MC_ERR_ARG;
+  if (audio_len) *audio_len = p->audio_len[slot];
+  if (code_len) *code_len = p->code_len[slot];
+  return MC_OK;
+}
+
+int mc_pool_set_graphs(mc_pool* p, int32_t enabled) {
+  if (!p) return MC_ERR_ARG;
+  p->use_graphs = enabled != 0;
+  if (!enabled) {
+    for (auto& kv : p->graphs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    p->graphs.clear();
+  }
+  return MC_OK;
+}
+
+/* chunks: HOST fp32 [n][C][len]; codes_out: HOST int64 [n][C][keep] (keep = keep_frames, or every frame when 0). */
+int mc_pool_push_audio(mc_pool* p, const int32_t* slots, int32_t n, const float* chunks, int32_t len, int32_t keep_frames,
+                       int64_t* codes_out, int32_t* frames_out, mc_stream_t stream_) {
+  if (!p) return MC_ERR_ARG;
+  mc_handle* h = p->h;
+  MC_ENTER(h);
+  int old_len = 0;
+  MC_TRY(pool_check_slots(p, slots, n, p->audio_len, &old_len, "mc_pool_push_audio"));
+  if (!chunks || !codes_out || len < 1) return h->fail(MC_ERR_ARG, "mc_pool_push_audio: bad arguments");
+  if (len > p->cap_samples) return h->fail(MC_ERR_ARG, "mc_pool_push_audio: chunk of %d samples exceeds the capacity %d", len, p->cap_samples);
+  MC_CUDA(h, cudaEventRecord(p->order_ev, (cudaStream_t)stream_));
+  MC_CUDA(h, cudaStreamWaitEvent(p->own, p->order_ev, 0));
+  cudaStream_t stream = p->own;
+  int hop = 1;
+  for (int i = 0; i < h->spec.n_convs; ++i) hop *= h->spec.conv_strides[i];
+  const int C = p->C, cap = p->cap_samples, rows = n * C;
+  const int new_len = std::min(old_len + len, std::max(len, p->ctx_samples));
+  const int keep_old = new_len - len;
+  const int F = (new_len + hop - 1) / hop;
+  const int keep = (keep_frames <= 0 || keep_frames > F) ? F : keep_frames;
+  for (int r = 0; r < rows; ++r) memcpy(p->pin_chunk + (size_t)r * cap, chunks + (size_t)r * len, (size_t)len * 4);
+  for (int j = 0; j < n; ++j) { p->pin_table[2 * j] = slots[j]; p->pin_table[2 * j + 1] = p->acur[slots[j]]; }
+  auto body = [&]() -> int {
+    MC_CUDA(h, cudaMemcpyAsync(p->dev_table, p->pin_table, (size_t)n * 8, cudaMemcpyHostToDevice, stream));
+    MC_CUDA(h, cudaMemcpy2DAsync(p->dev_chunk, (size_t)cap * 4, p->pin_chunk, (size_t)cap * 4, (size_t)len * 4, rows, cudaMemcpyHostToDevice, stream));
+    pool_roll_kernel<float><<<dim3((new_len + 255) / 256, rows), 256, 0, stream>>>(p->dev_table, C, cap, old_len, keep_old, len, p->audio[0],
+                                                                                  p->audio[1], p->dev_chunk, p->batch_audio, cap);
+    MC_LAUNCH_CHECK(h, "pool_roll_kernel");
+    MC_TRY(encode_impl(h, p->batch_audio, cap, rows, new_len, keep, p->dev_codes_out, nullptr, nullptr, stream));
+    MC_CUDA(h, cudaMemcpyAsync(p->pin_codes_out, p->dev_codes_out, (size_t)rows * keep * 8, cudaMemcpyDeviceToHost, stream));
+    return MC_OK;
+  };
+  MC_TRY(run_or_replay(p, std::make_tuple(0, old_len, len, keep, n), stream, body));
+  MC_CUDA(h, cudaStreamSynchronize(stream));
+  memcpy(codes_out, p->pin_codes_out, (size_t)rows * keep * 8);
+  if (frames_out) *frames_out = keep;
+  for (int j = 0; j < n; ++j) { p->acur[slots[j]] ^= 1; p->audio_len[slots[j]] = new_len; }
+  return MC_OK;
+}
+
+/* codes: HOST int64 [n][C][len]; wav_out: HOST fp32 [n][C][keep] (keep = keep_samples, or the whole window when 0). */
+int mc_pool_push_codes(mc_pool* p, const int32_t* slots, int32_t n, const int64_t* codes, int32_t len, int32_t keep_samples,
+                       float* wav_out, int32_t* samples_out, mc_stream_t stream_) {
+  if (!p) return MC_ERR_ARG;
+  mc_handle* h = p->h;
+  MC_ENTER(h);
+  int old_len = 0;
+  MC_TRY(pool_check_slots(p, slots, n, p->code_len, &old_len, "mc_pool_push_codes"));
+  if (!codes || !wav_out || len < 1) return h->fail(MC_ERR_ARG, "mc_pool_push_codes: bad arguments");
+  if (len > p->cap_frames) return h->fail(MC_ERR_ARG, "mc_pool_push_codes: %d frames exceed the capacity %d", len, p->cap_frames);
+  MC_CUDA(h, cudaEventRecord(p->order_ev, (cudaStream_t)stream_));
+  MC_CUDA(h, cudaStreamWaitEvent(p->own, p->order_ev, 0));
+  cudaStream_t stream = p->own;
+  int hop = 1;
+  for (int i = 0; i < h->spec.n_convs; ++i) hop *= h->spec.conv_strides[i];
+  const int C = p->C, cap = p->cap_frames, rows = n * C;
+  const int new_len = std::min(old_len + len, std::max(len, p->ctx_frames));
+  const int keep_old = new_len - len;
+  const int total = new_len * hop;
+  const int keep = (keep_samples <= 0 || keep_samples > total) ? total : keep_samples;
+  for (int r = 0; r < rows; ++r) memcpy(p->pin_codes_in + (size_t)r * cap, codes + (size_t)r * len, (size_t)len * 8);
+  for (int j = 0; j < n; ++j) { p->pin_table[2 * j] = slots[j]; p->pin_table[2 * j + 1] = p->ccur[slots[j]]; }
+  auto body = [&]() -> int {
+    MC_CUDA(h, cudaMemcpyAsync(p->dev_table, p->pin_table, (size_t)n * 8, cudaMemcpyHostToDevice, stream));
+    MC_CUDA(h, cudaMemcpy2DAsync(p->dev_codes_in, (size_t)cap * 8, p->pin_codes_in, (size_t)cap * 8, (size_t)len * 8, rows, cudaMemcpyHostToDevice, stream));
+    pool_roll_kernel<long long><<<dim3((new_len + 255) / 256, rows), 256, 0, stream>>>(
+        p->dev_table, C, cap, old_len, keep_old, len, reinterpret_cast<long long*>(p->codes[0]), reinterpret_cast<long long*>(p->codes[1]),
+        reinterpret_cast<const long long*>(p->dev_codes_in), reinterpret_cast<long long*>(p->batch_codes), new_len);
+    MC_LAUNCH_CHECK(h, "pool_roll_kernel");
+    MC_TRY(decode_impl(h, p->batch_codes, nullptr, rows, new_len, keep, p->dev_wav_out, stream));
+    MC_CUDA(h, cudaMemcpyAsync(p->pin_wav_out, p->dev_wav_out, (size_t)rows * keep * 4, cudaMemcpyDeviceToHost, stream));
+    return MC_OK;
+  };
+  MC_TRY(run_or_replay(p, std::make_tuple(1, old_len, len, keep, n), stream, body));
+  MC_CUDA(h, cudaStreamSynchronize(stream));
+  memcpy(wav_out, p->pin_wav_out, (size_t)rows * keep * 4);
+  if (samples_out) *samples_out = keep;
+  for (int j = 0; j < n; ++j) { p->ccur[slots[j]] ^= 1; p->code_len[slots[j]] = new_len; }
   return MC_OK;
 }
 

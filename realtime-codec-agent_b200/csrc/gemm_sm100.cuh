@@ -45,6 +45,9 @@ struct GemmParams {
   int rope_period;  // position = rope_offset + (row within group) % rope_period
   int rope_offset;
   int one = 1;      // always 1; opaque to the compiler (see gemm_epilogue_slab_fast)
+  // split-K kernel only: the NEXT GEMM's weights, pulled into L2 while this kernel runs (they do not depend on it)
+  const void* prefetch_ptr = nullptr;
+  long long prefetch_bytes = 0;
 };
 
 constexpr int GEMM_BM = 128;

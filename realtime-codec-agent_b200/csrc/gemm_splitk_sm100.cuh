@@ -81,6 +81,16 @@ gemm_splitk_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     tmem_relinquish();
   }
   pdl_launch_dependents();
+  if (warp == 7 && lane == 0 && p.prefetch_bytes > 0) {
+    // this CTA's share of the next GEMM's weight matrix -> L2 (HBM streams ahead of the dependency chain)
+    constexpr long long kPiece = 32768;
+    const long long pieces = (p.prefetch_bytes + kPiece - 1) / kPiece;
+    for (long long i = blockIdx.x; i < pieces; i += gridDim.x) {
+      const long long off = i * kPiece;
+      const long long n = p.prefetch_bytes - off < kPiece ? p.prefetch_bytes - off : kPiece;
+      l2_prefetch_bulk(reinterpret_cast<const uint8_t*>(p.prefetch_ptr) + off, static_cast<uint32_t>(n & ~15LL));
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

@@ -141,4 +141,30 @@ embed_distance_kernel(const long long* __restrict__ ids, int n, long long vocab_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Session pool (TTS-server style multi-session batching, tts_server.py:59,158): the rolling contexts of
+// up to max_sessions sessions live in one [slot][channel][cap] ping-pong buffer.  ONE launch rolls the contexts of
+// the n sessions of a batch (kept tail of the old context ++ the staged new chunk, audio_tokenizer.py:72-74 /
+// :111-113) and gathers them into the dense [n*C, ld] batch the encoder / decoder reads.
+//   table[2j] = slot of batch item j, table[2j+1] = which of the two context buffers currently holds it
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+pool_roll_kernel(const int* __restrict__ table, int C, int cap, int old_len, int keep_old, int n_new, T* __restrict__ ctx0,
+                 T* __restrict__ ctx1, const T* __restrict__ staged /*[n*C, cap]*/, T* __restrict__ batch, int batch_ld) {
+  const int jc = blockIdx.y;                                   // batch row = j*C + c
+  const int j = jc / C, c = jc - j * C;
+  const int slot = table[2 * j], par = table[2 * j + 1];
+  const T* src = (par ? ctx1 : ctx0) + (static_cast<long long>(slot) * C + c) * cap;
+  T* dst = (par ? ctx0 : ctx1) + (static_cast<long long>(slot) * C + c) * cap;
+  const T* st = staged + static_cast<long long>(jc) * cap;
+  T* bt = batch + static_cast<long long>(jc) * batch_ld;
+  const int new_len = keep_old + n_new;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < new_len; i += gridDim.x * blockDim.x) {
+    const T v = i < keep_old ? src[old_len - keep_old + i] : st[i - keep_old];
+    dst[i] = v;
+    bt[i] = v;
+  }
+}
+
 }  // namespace mc

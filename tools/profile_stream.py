@@ -13,6 +13,8 @@ import realtime_codec_agent_b200 as pkg
 
 spec = pkg.DEFAULT_SPEC
 gen = pkg.B200Generator(spec, pkg.init_random_weights(spec, seed=0), device="cuda")
+if "nosplit" not in sys.argv:
+    gen.set_option("small_m_split_k", 2)      # the kernels a streaming session uses (direct launches here, for the launch list)
 wav = pkg.synth_audio(32000, device="cuda")[None]
 codes = gen.encode(wav)
 for _ in range(3):
@@ -29,7 +31,7 @@ ev[2].record()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print(f"direct launches: encode {ev[0].elapsed_time(ev[1]) * 1e3:.0f} us, decode {ev[1].elapsed_time(ev[2]) * 1e3:.0f} us")
-if len(sys.argv) > 1 and sys.argv[1] == "graph":
+if "graph" in sys.argv:
     sess = gen.open_stream(1, 32000)
     w = pkg.synth_audio(64000).numpy()
     for i in range(150):
