@@ -1,16 +1,16 @@
-// Fused sliding-window attention on tcgen05, head_dim 64, causal window (keys j in [i-wl, i],
-// wl <= 32).  One CTA = 128 queries of one (window, head):
+// Fused sliding-window attention on tcgen05, head_dim 64, causal window (keys j in [i-wl, i], wl <= 32).
 //
-//   TMA   Q[128x64], K[160x64], V[160x64]  (keys q0-32 .. q0+127; out-of-tensor rows zero-filled)
-//   UMMA  S = Q K^T            128 x 160 x 64  -> TMEM cols [0,160)      (K-major A and B)
-//   SIMT  mask + softmax, one thread per query row, two passes over TMEM (max, then exp/sum);
-//         P (bf16) is written straight into the 128B-swizzled K-major layout UMMA reads
-//   UMMA  O = P V              128 x 64 x 160  -> TMEM cols [160,224)    (B = V, MN-major)
+//   TMA   Q[128x64], K[NKVx64], V[NKVx64] per (window, head, 128-query tile) through a ring of stages
+//   UMMA  S = Q K^T            128 x NKV x 64 -> TMEM                    (K-major A and B)
+//   SIMT  mask + softmax from TMEM, one thread per query row; P (bf16 pairs) goes back into TENSOR memory over the
+//         dead S columns (v4, default) or into a 128B-swizzled shared-memory tile (v3, kept for A/B runs)
+//   UMMA  O = P V              128 x 64 x NKV                             (A from TMEM in v4; B = V, MN-major)
 //   SIMT  O / rowsum -> bf16 -> global
 //
-// S and P never touch HBM.  A window of <= 128 frames (every streaming / offline window: 100) is a
-// single tile; longer one-shot inputs tile along F with the 32-key halo.  ~105 KB smem and 256 TMEM
-// columns per CTA -> two CTAs per SM overlap each other's serial phases.
+// S and P never touch HBM.  A window of <= 128 frames (every streaming / offline window: 100) is a single tile with
+// NKV = 128; longer one-shot inputs tile along F with a 32-key halo (NKV = 160).  Round 1's first two versions (one
+// item per CTA; two-slot pipeline without staged loads) were removed in round 2: v3 and v4 compute the same values in
+// the same order (tests/test_gpu_ops.py keeps v4 == v3 bit for bit, and both against the SIMT cross-check kernel).
 #pragma once
 #include "engine_common.cuh"
 #include "gemm_sm100.cuh"
@@ -19,425 +19,18 @@ namespace mc {
 
 constexpr int ATT_BQ = 128;    // queries per CTA
 constexpr int ATT_HALO = 32;   // keys before the first query
-constexpr int ATT_NKV = ATT_BQ + ATT_HALO;  // 160
-constexpr int ATT_THREADS = 128;
 constexpr int ATT_SMEM_Q = ATT_BQ * 128;        // 16384
-constexpr int ATT_SMEM_KV = ATT_NKV * 128;      // 20480
-constexpr int ATT_SMEM_P = 3 * ATT_BQ * 128;    // three 64-key atoms (the third half used)
-constexpr int ATT_SMEM_BYTES = ATT_SMEM_Q + 2 * ATT_SMEM_KV + ATT_SMEM_P + 64 + 1024;
-constexpr int ATT_TMEM_COLS = 256;
+constexpr int ATT2_TMEM_COLS = 512;             // the persistent kernels allocate the whole tensor memory of their SM
 
 inline bool attn_sm100_supported(int wl, int wr) { return wr == 0 && wl <= ATT_HALO; }
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
-attention_window_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                              __nv_bfloat16* __restrict__ out, int F, int H, int wl, int out_rows,
-                              float scale_log2e) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + ATT_SMEM_Q;
-  uint8_t* sV = sK + ATT_SMEM_KV;
-  uint8_t* sP = sV + ATT_SMEM_KV;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + ATT_SMEM_P);  // [0] tma, [1] S ready, [2] O ready
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
-
-  const int warp = threadIdx.x >> 5;
-  const int q_tiles = (F + ATT_BQ - 1) / ATT_BQ;
-  const int q0 = (blockIdx.x % q_tiles) * ATT_BQ;
-  const int h = (blockIdx.x / q_tiles) % H;
-  const int b = blockIdx.x / (q_tiles * H);
-  const int d = H * 64;
-  const int first_out = F - out_rows;             // only queries >= first_out are stored (dead-output elimination)
-  if (q0 + ATT_BQ <= first_out) return;           // uniform: nothing of this tile is kept
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&map_q);
-    tma_prefetch_desc(&map_kv);
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_init(&bars[2], 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) {
-    tmem_alloc(tmem_ptr, ATT_TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_s = tmem_base;
-  const uint32_t tmem_o = tmem_base + ATT_NKV;
-
-  if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(&bars[0], ATT_SMEM_Q + 2 * ATT_SMEM_KV);
-    const int row_q = b * F + q0;
-    tma_load_2d(sQ, &map_q, &bars[0], h * 64, row_q);
-    tma_load_2d(sK, &map_kv, &bars[0], d + h * 64, row_q - ATT_HALO);
-    tma_load_2d(sV, &map_kv, &bars[0], 2 * d + h * 64, row_q - ATT_HALO);
-    mbar_wait(&bars[0], 0);
-    tc_fence_after();
-    constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, ATT_NKV, 0, 0);
-    const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ), 1024, 16);
-    const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sK), 1024, 16);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_s, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-    umma_commit(&bars[1]);
-  }
-  __syncwarp();
-
-  // ---- softmax: thread r owns query row q0 + r
-  const int r = threadIdx.x;
-  const int qi = q0 + r;
-  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-  mbar_wait(&bars[1], 0);
-  tc_fence_after();
-  // key column c <-> key index kj = q0 - HALO + c; valid iff 0 <= kj < F and qi - wl <= kj <= qi
-  const int c_lo = max(r + ATT_HALO - wl, ATT_HALO - q0);  // first valid column
-  const int c_hi = (qi < F) ? (r + ATT_HALO) : -1;         // last valid column (causal); none for padded rows
-  // columns any row of this warp can attend: [32*warp + HALO - wl, 32*warp + HALO + 31]
-  const int wc_lo = warp * 32 + ATT_HALO - wl, wc_hi = warp * 32 + ATT_HALO + 31;
-  float mx = -INFINITY;
-#pragma unroll 1
-  for (int c0 = 0; c0 < ATT_NKV; c0 += 32) {
-    if (c0 + 31 < wc_lo || c0 > wc_hi) continue;  // warp-uniform: fully masked chunk
-    uint32_t raw[32];
-    tmem_ld_32x32b_x32(tmem_s + lane_addr + c0, raw);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int c = c0 + j;
-      if (c >= c_lo && c <= c_hi) mx = fmaxf(mx, __uint_as_float(raw[j]));
-    }
-  }
-  const float mscaled = (mx == -INFINITY) ? 0.0f : mx * scale_log2e;
-  float sum = 0.0f;
-#pragma unroll 1
-  for (int c0 = 0; c0 < ATT_NKV; c0 += 32) {
-    uint8_t* atom = sP + (c0 >> 6) * (ATT_BQ * 128) + r * 128;
-    const int chunk0 = (c0 & 63) >> 3;
-    if (c0 + 31 < wc_lo || c0 > wc_hi) {          // fully masked for the whole warp: P = 0, no TMEM read
-#pragma unroll
-      for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(atom + (((chunk0 + u) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
-      continue;
-    }
-    uint32_t raw[32];
-    tmem_ld_32x32b_x32(tmem_s + lane_addr + c0, raw);
-    tmem_ld_wait();
-    uint32_t packed[16];
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      const int c = c0 + j;
-      float p0 = 0.0f, p1 = 0.0f;
-      if (c >= c_lo && c <= c_hi) p0 = exp2f(__uint_as_float(raw[j]) * scale_log2e - mscaled);
-      if (c + 1 >= c_lo && c + 1 <= c_hi) p1 = exp2f(__uint_as_float(raw[j + 1]) * scale_log2e - mscaled);
-      sum += p0 + p1;
-      packed[j >> 1] = pack_bf16x2(p0, p1);
-    }
-    // 32 keys = 4 chunks of 16 bytes inside atom (c0 / 64), chunk index ((c0 % 64) / 8 + u) ^ (r & 7)
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int chunk = (chunk0 + u) ^ (r & 7);
-      *reinterpret_cast<uint4*>(atom + chunk * 16) =
-          make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
-    }
-  }
-  fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor core (async proxy)
-  tc_fence_before();
-  __syncthreads();
-
-  if (threadIdx.x == 0) {
-    tc_fence_after();
-    constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, 64, 0, 1);  // B = V is MN-major
-#pragma unroll
-    for (int k = 0; k < ATT_NKV / 16; ++k) {
-      // A: P atom (k / 4), 32 bytes per 16-key step inside the atom
-      const uint64_t pdesc = umma_smem_desc_sw128(smem_u32(sP + (k >> 2) * (ATT_BQ * 128)) + (k & 3) * 32, 1024, 16);
-      // B: V rows are keys; 16 keys = 2048 bytes per step
-      const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sV) + k * 2048, 1024, 1024);
-      umma_bf16_ss(tmem_o, pdesc, vdesc, idesc_o, k != 0);
-    }
-    umma_commit(&bars[2]);
-  }
-  __syncwarp();
-  mbar_wait(&bars[2], 0);
-  tc_fence_after();
-  {
-    uint32_t raw0[32], raw1[32];
-    tmem_ld_32x32b_x32(tmem_o + lane_addr, raw0);
-    tmem_ld_32x32b_x32(tmem_o + lane_addr + 32, raw1);
-    tmem_ld_wait();
-    if (qi < F && qi >= first_out) {
-      const float inv = 1.0f / sum;
-      __nv_bfloat16* o = out + (static_cast<long long>(b) * out_rows + (qi - first_out)) * d + h * 64;
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 w;
-        w.x = pack_bf16x2(__uint_as_float(raw0[j]) * inv, __uint_as_float(raw0[j + 1]) * inv);
-        w.y = pack_bf16x2(__uint_as_float(raw0[j + 2]) * inv, __uint_as_float(raw0[j + 3]) * inv);
-        w.z = pack_bf16x2(__uint_as_float(raw0[j + 4]) * inv, __uint_as_float(raw0[j + 5]) * inv);
-        w.w = pack_bf16x2(__uint_as_float(raw0[j + 6]) * inv, __uint_as_float(raw0[j + 7]) * inv);
-        *reinterpret_cast<uint4*>(o + j) = w;
-      }
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 w;
-        w.x = pack_bf16x2(__uint_as_float(raw1[j]) * inv, __uint_as_float(raw1[j + 1]) * inv);
-        w.y = pack_bf16x2(__uint_as_float(raw1[j + 2]) * inv, __uint_as_float(raw1[j + 3]) * inv);
-        w.z = pack_bf16x2(__uint_as_float(raw1[j + 4]) * inv, __uint_as_float(raw1[j + 5]) * inv);
-        w.w = pack_bf16x2(__uint_as_float(raw1[j + 6]) * inv, __uint_as_float(raw1[j + 7]) * inv);
-        *reinterpret_cast<uint4*>(o + 32 + j) = w;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, ATT_TMEM_COLS);
-  }
-}
-
+// Softmax details shared by v3 / v4: each softmax thread needs only the 64 score columns its row can see, read once
+// from TMEM; masking is branch-free (masked scores become -inf, exp2 gives 0) and the row sum is accumulated strictly in
+// ascending key order, so results do not depend on where a window was cut for dead-output elimination (adding the exact
+// zeros of masked keys is a no-op); P*V sums keys in 16-key UMMA groups.
+//
 // =============================================================================================
-// v2: persistent, two-slot pipelined version of the same computation.  One CTA per SM walks the
-// (window, head, query-tile) items; while the four softmax warps work on item i in slot i&1, the
-// TMA warp is already loading item i+1 into the other slot and the MMA warp has issued its S=QK^T.
-//   warps 0-3 / 4-7  softmax+output of slot 0 / slot 1:  p_full[s], slot_free[s] <- s_full[s], o_full[s]
-//   warp 8  TMA producer      kv_full[s]   (tx)      <- slot_free[s]
-//   warp 9  MMA issuer        s_full[s], o_full[s]   <- kv_full[s], p_full[s]
-//   (issuer warps carry the highest warp ids: the sub-partition arbiter prefers them)
-// The two softmax groups ping-pong: while one waits for its P*V to retire, the other is in its
-// softmax.  Each softmax thread needs only the 64 score columns its row can see (32q .. 32q+63),
-// read once from TMEM.  Masking is branch-free (masked scores become -inf, exp2 gives 0) and the row
-// sum is accumulated strictly in ascending key order so that results do not depend on where the
-// window was cut for dead-output elimination (adding the exact zeros of masked keys is a no-op).
-// =============================================================================================
-constexpr int ATT2_THREADS = 320;
-constexpr int ATT2_SLOT_BYTES = ATT_SMEM_Q + 2 * ATT_SMEM_KV + ATT_SMEM_P;   // 106496
-constexpr int ATT2_SMEM_BYTES = 2 * ATT2_SLOT_BYTES + 256 + 1024;
-constexpr int ATT2_TMEM_COLS = 512;
 
-__global__ void __launch_bounds__(ATT2_THREADS, 1)
-attention_window_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                                 __nv_bfloat16* __restrict__ out, int B, int F, int H, int wl, int out_rows,
-                                 float scale_log2e) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * ATT2_SLOT_BYTES);
-  uint64_t* kv_full = bars;        // [2]
-  uint64_t* s_full = bars + 2;     // [2]
-  uint64_t* p_full = bars + 4;     // [2]
-  uint64_t* o_full = bars + 6;     // [2]
-  uint64_t* slot_free = bars + 8;  // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int d = H * 64;
-  const int first_out = F - out_rows;
-  const int q_tiles = (F + ATT_BQ - 1) / ATT_BQ;
-  const int first_tile = first_out / ATT_BQ;          // query tiles before it hold no kept row
-  const int kept_tiles = q_tiles - first_tile;
-  const int n_items = B * H * kept_tiles;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&map_q);
-    tma_prefetch_desc(&map_kv);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 4);
-      mbar_init(&o_full[s], 1);
-      mbar_init(&slot_free[s], 4);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 9) {
-    tmem_alloc(tmem_ptr, ATT2_TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 8) {
-    if (lane == 0) {
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int s = it & 1;
-        const uint32_t use = (it >> 1) & 1;
-        const int qt = first_tile + item % kept_tiles;
-        const int h = (item / kept_tiles) % H;
-        const int b = item / (kept_tiles * H);
-        uint8_t* slot = smem + s * ATT2_SLOT_BYTES;
-        mbar_wait(&slot_free[s], use ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], ATT_SMEM_Q + 2 * ATT_SMEM_KV);
-        const int row_q = b * F + qt * ATT_BQ;
-        tma_load_2d(slot, &map_q, &kv_full[s], h * 64, row_q);
-        tma_load_2d(slot + ATT_SMEM_Q, &map_kv, &kv_full[s], d + h * 64, row_q - ATT_HALO);
-        tma_load_2d(slot + ATT_SMEM_Q + ATT_SMEM_KV, &map_kv, &kv_full[s], 2 * d + h * 64, row_q - ATT_HALO);
-      }
-    }
-  } else if (warp == 9) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, ATT_NKV, 0, 0);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, 64, 0, 1);
-      const int my_items = (n_items > static_cast<int>(blockIdx.x)) ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-      // Each slot alternates  S(it) -> P*V(it) -> S(it+2) -> ...; the two slots progress independently,
-      // so the single issuing thread polls both and issues whatever is ready.
-      int cur[2] = {0, 1};
-      bool need_pv[2] = {false, false};
-      int remaining = 2 * my_items;  // MMA groups still to issue
-      const long long t0 = clock64();
-      while (remaining > 0) {
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (cur[s] >= my_items) continue;
-          const uint32_t use = (cur[s] >> 1) & 1;
-          uint8_t* slot = smem + s * ATT2_SLOT_BYTES;
-          if (!need_pv[s]) {
-            if (!mbar_try_wait(&kv_full[s], use)) continue;
-            tc_fence_after();
-            const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(slot), 1024, 16);
-            const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(slot + ATT_SMEM_Q), 1024, 16);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + s * 256, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-            umma_commit(&s_full[s]);
-            need_pv[s] = true;
-            --remaining;
-          } else {
-            if (!mbar_try_wait(&p_full[s], use)) continue;
-            tc_fence_after();
-            uint8_t* sV = slot + ATT_SMEM_Q + ATT_SMEM_KV;
-            uint8_t* sP = sV + ATT_SMEM_KV;
-#pragma unroll
-            for (int k = 0; k < ATT_NKV / 16; ++k) {
-              const uint64_t pdesc = umma_smem_desc_sw128(smem_u32(sP + (k >> 2) * (ATT_BQ * 128)) + (k & 3) * 32, 1024, 16);
-              const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sV) + k * 2048, 1024, 1024);
-              umma_bf16_ss(tmem_base + s * 256 + ATT_NKV, pdesc, vdesc, idesc_o, k != 0);
-            }
-            umma_commit(&o_full[s]);
-            need_pv[s] = false;
-            cur[s] += 2;
-            --remaining;
-          }
-        }
-        if (clock64() - t0 > 8000000000LL) {
-          printf("attention v2: MMA issuer timeout, block %d\n", blockIdx.x);
-          __trap();
-        }
-      }
-    }
-  } else {
-    const int group = warp >> 2;               // softmax group = slot it serves (warps 0-3 / 4-7)
-    const int q = warp & 3;                    // TMEM lane quarter
-    const int r = q * 32 + lane;               // query row inside the tile
-    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const int s = group;
-    uint8_t* slot = smem + s * ATT2_SLOT_BYTES;
-    uint8_t* sP = slot + ATT_SMEM_Q + 2 * ATT_SMEM_KV;
-    const uint32_t tmem_s = tmem_base + s * 256;
-    const uint32_t tmem_o = tmem_s + ATT_NKV;
-    for (int it = group; blockIdx.x + static_cast<long long>(it) * gridDim.x < n_items; it += 2) {
-      const int item = blockIdx.x + it * gridDim.x;
-      const uint32_t use = (it >> 1) & 1;
-      const int qt = first_tile + item % kept_tiles;
-      const int h = (item / kept_tiles) % H;
-      const int b = item / (kept_tiles * H);
-      const int q0 = qt * ATT_BQ;
-      const int qi = q0 + r;
-
-      mbar_wait(&s_full[s], use);
-      tc_fence_after();
-      // this warp's rows see key columns 32q + HALO - wl .. 32q + HALO + 31, all inside [32q, 32q + 64)
-      uint32_t raw0[32], raw1[32];
-      tmem_ld_32x32b_x32(tmem_s + lane_addr + q * 32, raw0);
-      tmem_ld_32x32b_x32(tmem_s + lane_addr + q * 32 + 32, raw1);
-      tmem_ld_wait();
-      const int c_lo = max(r + ATT_HALO - wl, ATT_HALO - q0) - q * 32;   // relative to column 32q
-      const int c_hi = (qi < F) ? (r + ATT_HALO - q * 32) : -1;
-      float sc[64];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        sc[j] = (j >= c_lo && j <= c_hi) ? __uint_as_float(raw0[j]) * scale_log2e : -INFINITY;
-        sc[32 + j] = (j + 32 >= c_lo && j + 32 <= c_hi) ? __uint_as_float(raw1[j]) * scale_log2e : -INFINITY;
-      }
-#pragma unroll
-      for (int j = 0; j < 64; j += 2) mx = fmax3(mx, sc[j], sc[j + 1]);
-      const float mref = (mx == -INFINITY) ? 0.0f : mx;
-      float sum = 0.0f;
-      uint32_t pk[32];
-#pragma unroll
-      for (int j = 0; j < 64; j += 2) {   // ascending keys, one accumulator
-        float p0, p1;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(sc[j] - mref));
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(sc[j + 1] - mref));
-        sum += p0 + p1;
-        pk[j >> 1] = pack_bf16x2(p0, p1);
-      }
-      // P row (160 keys = 20 chunks of 16 B over three 64-key atoms): two live 32-key chunks, zeros elsewhere
-#pragma unroll
-      for (int c0 = 0; c0 < ATT_NKV; c0 += 32) {
-        uint8_t* atom = sP + (c0 >> 6) * (ATT_BQ * 128) + r * 128;
-        const int chunk0 = (c0 & 63) >> 3;
-        const int rel = (c0 >> 5) - q;  // 0 -> first live chunk, 1 -> second, else zero
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint4 w = make_uint4(0, 0, 0, 0);
-          if (rel == 0) w = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-          else if (rel == 1) w = make_uint4(pk[16 + 4 * u], pk[16 + 4 * u + 1], pk[16 + 4 * u + 2], pk[16 + 4 * u + 3]);
-          *reinterpret_cast<uint4*>(atom + (((chunk0 + u) ^ (r & 7)) << 4)) = w;
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[s]);
-
-      mbar_wait(&o_full[s], use);
-      tc_fence_after();
-      tmem_ld_32x32b_x32(tmem_o + lane_addr, raw0);
-      tmem_ld_32x32b_x32(tmem_o + lane_addr + 32, raw1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&slot_free[s]);   // TMEM and smem of this slot may be refilled
-      if (qi < F && qi >= first_out) {
-        const float inv = 1.0f / sum;
-        __nv_bfloat16* o = out + (static_cast<long long>(b) * out_rows + (qi - first_out)) * d + h * 64;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(raw0[j]) * inv, __uint_as_float(raw0[j + 1]) * inv);
-          w.y = pack_bf16x2(__uint_as_float(raw0[j + 2]) * inv, __uint_as_float(raw0[j + 3]) * inv);
-          w.z = pack_bf16x2(__uint_as_float(raw0[j + 4]) * inv, __uint_as_float(raw0[j + 5]) * inv);
-          w.w = pack_bf16x2(__uint_as_float(raw0[j + 6]) * inv, __uint_as_float(raw0[j + 7]) * inv);
-          *reinterpret_cast<uint4*>(o + j) = w;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(raw1[j]) * inv, __uint_as_float(raw1[j + 1]) * inv);
-          w.y = pack_bf16x2(__uint_as_float(raw1[j + 2]) * inv, __uint_as_float(raw1[j + 3]) * inv);
-          w.z = pack_bf16x2(__uint_as_float(raw1[j + 4]) * inv, __uint_as_float(raw1[j + 5]) * inv);
-          w.w = pack_bf16x2(__uint_as_float(raw1[j + 6]) * inv, __uint_as_float(raw1[j + 7]) * inv);
-          *reinterpret_cast<uint4*>(o + 32 + j) = w;
-        }
-      }
-    }
-  }
-  __syncwarp();
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, ATT2_TMEM_COLS);
-  }
-}
-
-// =============================================================================================
 // v3: v2 with the operand loads decoupled from the compute slots.
 //   * Q/K/V tiles travel through their own ring of TMA stages (3 deep for single-tile windows), so two
 //     items are always in flight towards an SM while a third is being consumed — v2 could only request
@@ -1041,41 +634,6 @@ inline int launch_attention_sm100_v3(mc_handle* h, const bf16* qkv, bf16* out, i
   }
   if (F <= ATT_BQ) return launch_attention_sm100_v3_nkv<128>(h, qkv, out, B, F, out_rows, stream);
   return launch_attention_sm100_v3_nkv<160>(h, qkv, out, B, F, out_rows, stream);
-}
-
-inline int launch_attention_sm100_v2(mc_handle* h, const bf16* qkv, bf16* out, int B, int F, int out_rows,
-                                     cudaStream_t stream) {
-  const mc_spec& s = h->spec;
-  const int d = s.d_model;
-  const CUtensorMap *mq, *mkv;
-  MC_TRY(mc_internal::get_map_2d_bf16(h, qkv, (uint64_t)3 * d, (uint64_t)B * F, 64, ATT_BQ, &mq));
-  MC_TRY(mc_internal::get_map_2d_bf16(h, qkv, (uint64_t)3 * d, (uint64_t)B * F, 64, ATT_NKV, &mkv));
-  MC_TRY(mc_allow_smem(h, attention_window_sm100_v2_kernel, ATT2_SMEM_BYTES));
-  const int q_tiles = (F + ATT_BQ - 1) / ATT_BQ;
-  const long long items = (long long)B * s.n_heads * (q_tiles - (F - out_rows) / ATT_BQ);
-  if (items > INT_MAX) return h->fail(MC_ERR_ARG, "attention: too many tiles");
-  const int grid = (int)std::min<long long>(items, h->num_sms);
-  attention_window_sm100_v2_kernel<<<grid, ATT2_THREADS, ATT2_SMEM_BYTES, stream>>>(
-      *mq, *mkv, out, B, F, s.n_heads, s.window_left, out_rows, 0.125f * 1.4426950408889634f);
-  MC_LAUNCH_CHECK(h, "attention_window_sm100_v2_kernel");
-  return MC_OK;
-}
-
-inline int launch_attention_sm100(mc_handle* h, const bf16* qkv, bf16* out, int B, int F, int out_rows,
-                                  cudaStream_t stream) {
-  const mc_spec& s = h->spec;
-  const int d = s.d_model;
-  const CUtensorMap *mq, *mkv;
-  MC_TRY(mc_internal::get_map_2d_bf16(h, qkv, (uint64_t)3 * d, (uint64_t)B * F, 64, ATT_BQ, &mq));
-  MC_TRY(mc_internal::get_map_2d_bf16(h, qkv, (uint64_t)3 * d, (uint64_t)B * F, 64, ATT_NKV, &mkv));
-  MC_TRY(mc_allow_smem(h, attention_window_sm100_kernel, ATT_SMEM_BYTES));
-  const long long blocks = (long long)((F + ATT_BQ - 1) / ATT_BQ) * s.n_heads * B;
-  if (blocks > INT_MAX) return h->fail(MC_ERR_ARG, "attention: too many tiles");
-  const dim3 grid((unsigned)blocks);
-  attention_window_sm100_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(*mq, *mkv, out, F, s.n_heads, s.window_left,
-                                                                            out_rows, 0.125f * 1.4426950408889634f);
-  MC_LAUNCH_CHECK(h, "attention_window_sm100_kernel");
-  return MC_OK;
 }
 
 }  // namespace mc

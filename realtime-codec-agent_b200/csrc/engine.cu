@@ -146,13 +146,19 @@ int launch_gemm_splitk_s(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   return MC_OK;
 }
 
-// S for a few-rows GEMM, or 0: the largest split (<= 8) that divides the k-blocks and keeps the grid within two CTAs per SM
+// S for a few-rows GEMM, or 0: the largest split (<= 8) that divides the k-blocks and keeps the grid within one CTA per
+// SM.  Only GEMMs with few output tiles are split: measured in a dependent chain at M = 100 (tools/diag_small_gemm.py,
+// profiles/r02_small_gemm_chain.log) Wo (16 tiles) goes 7.6 -> 6.3 us and W2 21.1 -> 8.1 us with S = 8, but QKV (48
+// tiles) and W1 (64) are FASTER on the plain one-CTA-per-tile kernel (7.7 us) than split 4 ways (9.0 us): the cluster
+// kernel's fixed cost (two cluster barriers, the DSMEM reduction at ~20 B/clk, two CTAs sharing an SM's tensor pipe)
+// exceeds what their short K = 1024 loop can give back.
 int pick_split_k(const mc_handle* h, const GemmCall& c) {
   if (c.M > 2 * GEMM_BM) return 0;
   const int base = ((c.M + GEMM_BM - 1) / GEMM_BM) * ((c.N + 63) / 64);
+  if (base > 32) return 0;
   const int num_kb = c.K / GEMM_BK;
   for (int s = 8; s >= 2; s >>= 1)
-    if (num_kb % s == 0 && base * s <= 2 * h->num_sms) return s;
+    if (num_kb % s == 0 && num_kb / s >= 2 && base * s <= h->num_sms) return s;
   return 0;
 }
 
@@ -231,18 +237,11 @@ int launch_attention(mc_handle* h, const bf16* qkv, bf16* out, int B, int F, int
   const double span = std::min(F, s.window_left + s.window_right + 1);
   McProfScope prof(h, 1, 4.0 * B * out_rows * span * s.d_model,
                    (double)B * (F * 2.0 + out_rows * 2.0) * s.d_model * 2.0, stream);
-  if (impl == 0 && attn_sm100_supported(s.window_left, s.window_right)) {
+  if (impl == 0 && attn_sm100_supported(s.window_left, s.window_right)) {   // v4 (P in tensor memory) or, with attn_p_tmem = 0, v3
     MC_TRY(launch_attention_sm100_v3(h, qkv, out, B, F, out_rows, stream));
     return MC_OK;
   }
-  if (impl == 3 && attn_sm100_supported(s.window_left, s.window_right)) {   // previous two-slot version (A/B timing)
-    MC_TRY(launch_attention_sm100_v2(h, qkv, out, B, F, out_rows, stream));
-    return MC_OK;
-  }
-  if (impl == 2 && attn_sm100_supported(s.window_left, s.window_right)) {   // one-item-per-CTA version (A/B timing)
-    MC_TRY(launch_attention_sm100(h, qkv, out, B, F, out_rows, stream));
-    return MC_OK;
-  }
+  if (impl != 0 && impl != 1) return h->fail(MC_ERR_ARG, "attention: unknown implementation %d (0 = tcgen05, 1 = SIMT cross-check)", impl);
   if (s.window_left + s.window_right + 1 > 160) return h->fail(MC_ERR_ARG, "attention window too wide");
   const long long warps = (long long)B * F * s.n_heads;
   const int threads = 256;
@@ -867,6 +866,7 @@ int mc_set_option(mc_handle* h, const char* key, int32_t value) {
   else if (k == "fast_epilogue") h->fast_epilogue = value != 0;
   else if (k == "pdl") h->pdl = value != 0;
   else if (k == "attn_p_tmem") h->attn_p_tmem = value != 0;
+  else if (k == "debug_repeat") h->debug_repeat = value;   // mc_op_* launch their kernel `value` times back to back (timing tools)
   else if (k == "l2_prefetch") { h->l2_prefetch = value != 0; h->tensor_gen++; }
   else if (k == "small_m_split_k") {   // 0 never, 1 streaming sessions only (default), 2 every GEMM of <= 256 rows
     if (value < 0 || value > 2) return h->fail(MC_ERR_ARG, "mc_set_option: small_m_split_k is 0, 1 or 2");
@@ -884,7 +884,7 @@ int mc_set_option(mc_handle* h, const char* key, int32_t value) {
 int mc_set_debug_impl(mc_handle* h, int32_t attention_impl, int32_t vq_impl) {
   if (!h) return MC_ERR_ARG;
   h->gemm_pair = (attention_impl & 4) ? 0 : 1;   // bit 2: force the single-CTA GEMM (A/B measurements)
-  attention_impl &= 3;
+  attention_impl &= 1;
   h->attn_impl = attention_impl;
   h->vq_impl = vq_impl;
   return MC_OK;
@@ -902,17 +902,21 @@ int mc_op_gemm(mc_handle* h, const void* A, int64_t a_rows, int32_t a_k_wrap, co
   g.grp_in = grp_in > 0 ? grp_in : INT_MAX; g.grp_valid = grp_in > 0 ? grp_valid : INT_MAX;
   g.grp_stride = grp_stride; g.grp_off = grp_off;
   g.rope_cols = rope_cols; g.rope_period = rope_period; g.block_n = block_n;
+  for (int r = 1; r < h->debug_repeat; ++r) MC_TRY(launch_gemm(h, g, (cudaStream_t)stream));   // back-to-back chain (timing)
   return launch_gemm(h, g, (cudaStream_t)stream);
 }
 
 int mc_op_rmsnorm(mc_handle* h, const float* x, const float* gamma, void* out_bf16, int32_t M, int32_t d,
                   mc_stream_t stream) {
   MC_ENTER(h);
+  for (int r = 1; r < h->debug_repeat; ++r) MC_TRY(launch_rmsnorm(h, x, gamma, reinterpret_cast<bf16*>(out_bf16), M, d, INT_MAX, 0, 0, (cudaStream_t)stream));
   return launch_rmsnorm(h, x, gamma, reinterpret_cast<bf16*>(out_bf16), M, d, INT_MAX, 0, 0, (cudaStream_t)stream);
 }
 
 int mc_op_attention(mc_handle* h, const void* qkv, void* out, int32_t B, int32_t F, int32_t impl, mc_stream_t stream) {
   MC_ENTER(h);
+  for (int r = 1; r < h->debug_repeat; ++r)
+    MC_TRY(launch_attention(h, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, F, F, impl, (cudaStream_t)stream));
   return launch_attention(h, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, F, F, impl,
                           (cudaStream_t)stream);
 }

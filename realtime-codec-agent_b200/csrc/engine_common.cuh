@@ -68,6 +68,7 @@ struct mc_handle {
   // sessions (the latency path; stateless mc_encode / mc_decode stay batch-invariant), 2 always
   int split_k = 1;
   bool in_session = false;
+  int debug_repeat = 1;
   bool l2_prefetch = true;    // split-K GEMMs pull the next GEMM's weights into L2 while they run
   bool pdl = true;            // programmatic dependent launch between consecutive kernels of a pass
   bool shared_stem = true;  // overlapping hop-aligned windows share one pass of the conv stack (exact)

@@ -232,7 +232,7 @@ def test_rmsnorm(gen):
     assert (out.float() - ref).abs().max().item() < 0.03
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2, 3])
+@pytest.mark.parametrize("impl", [0, 1])
 @pytest.mark.parametrize("B,Fr", [(1, 100), (3, 100), (2, 37), (1, 128), (2, 300), (40, 100)])
 def test_window_attention(gen, impl, B, Fr):
     d, H = gen.spec.d_model, gen.spec.n_heads
@@ -250,14 +250,12 @@ def test_window_attention(gen, impl, B, Fr):
 
 
 @pytest.mark.parametrize("B,Fr", [(1, 100), (5, 100), (300, 100), (2, 128), (3, 129), (2, 300), (1, 7)])
-def test_attention_v3_is_bit_identical_to_v2(gen, B, Fr):
-    """The default kernel (v4: staged loads, P in tensor memory, three compute slots), the shared-memory-P kernel (v3) and
-    the two-slot kernel (v2) differ in scheduling and operand placement only: same masks, same ex2, same key-group sums."""
+def test_attention_v4_is_bit_identical_to_v3(gen, B, Fr):
+    """The default kernel (v4: staged loads, P in tensor memory, three compute slots) and the shared-memory-P kernel (v3)
+    differ in scheduling and operand placement only: same masks, same ex2, same key-group sums."""
     d = gen.spec.d_model
     qkv = _rand((B * Fr, 3 * d), seed=19).to(torch.bfloat16)
     a = gen.op_attention(qkv, B, Fr, impl=0)
-    b = gen.op_attention(qkv, B, Fr, impl=3)
-    assert torch.equal(a, b)
     assert torch.equal(a, gen.op_attention(qkv, B, Fr, impl=0))
     try:
         gen.set_option("attn_p_tmem", 0)

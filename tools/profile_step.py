@@ -45,13 +45,13 @@ if only_default:
     run("default", iters=1)
     torch.cuda.profiler.stop()
 else:
-    gen.set_debug_impl(attention=3)
-    c2 = run("attention v2 (no staged loads)")
-    gen.set_debug_impl(attention=0)
+    gen.set_option("attn_p_tmem", 0)
+    c2 = run("attention v3 (P through shared memory)")
+    gen.set_option("attn_p_tmem", 1)
     gen.set_option("shared_stem", 0)
     c3 = run("conv stack per window (shared_stem=0)")
     gen.set_option("shared_stem", 1)
-    print("attention v3 == v2:", bool(torch.equal(codes, c2)), " shared stem == per-window:", bool(torch.equal(codes, c3)))
+    print("attention v4 == v3:", bool(torch.equal(codes, c2)), " shared stem == per-window:", bool(torch.equal(codes, c3)))
 print("checksum", int(codes.sum()), "audio_hash", float(wav.double().sum()))
 again = gen.encode(wav, keep_last_frames=5, row_stride=1600, num_windows=B, window_samples=32000)
 full = gen.encode(wav[: 256 * 1600 + 32000], keep_last_frames=0, row_stride=1600, num_windows=256, window_samples=32000)
