@@ -103,6 +103,9 @@ int mc_vq_search(mc_handle* h, const float* z, int32_t M, int64_t* codes, float*
 /* Copies the cached projected codebook, fp32 [K, dq]. */
 int mc_codebook(mc_handle* h, float* out, mc_stream_t stream);
 
+/* Debug: timeline of a pass (only in a library built with -DMC_TRACE; MC_ERR_STATE otherwise). */
+int64_t mc_debug_trace(mc_handle* h, void* dev_buf, int64_t capacity_records);
+
 /* ---- corpus ingest on the device: what _prep_audio_for_tokenization (audio_tokenizer.py:203-215: int16 -> float,
  * librosa.to_mono, librosa.resample) and the offline CLI's loader do on the host in the reference.
  * pcm: DEVICE pointer to interleaved frames [frames][channels] in `format`; out: planar fp32 [C_out, out_ld]

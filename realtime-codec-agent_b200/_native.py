@@ -46,6 +46,7 @@ SYMBOLS = {
     "mc_vq_search": (C.c_int, [_P, _P, _I32, _P, _P, _P]),
     "mc_codebook": (C.c_int, [_P, _P, _P]),
     "mc_launch_count": (_I64, [_P]),
+    "mc_debug_trace": (_I64, [_P, _P, _I64]),
     "mc_set_debug_impl": (C.c_int, [_P, _I32, _I32]),
     "mc_set_option": (C.c_int, [_P, C.c_char_p, _I32]),
     "mc_profile_begin": (C.c_int, [_P]),
@@ -89,7 +90,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("MAGICODEC_B200_LIB") or LIB_PATH     # the env override is for diagnostic builds (build.py --trace)
     if not os.path.isfile(path):
         raise RuntimeError(
             f"{path} is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -38,18 +38,22 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found; the B200 engine cannot be built")
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    digest = _sources_digest()
-    if not force and os.path.isfile(LIB_PATH) and os.path.isfile(_STAMP):
-        with open(_STAMP) as f:
+def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+    """trace=True adds -DMC_TRACE (kernels log their dependency-wait times; tools/trace_stream.py) — a diagnostic build,
+    written next to the shipped library as libmagicodec_b200_trace.so and loaded only when $MAGICODEC_B200_LIB names it."""
+    digest = _sources_digest() + ("+trace" if trace else "")
+    lib_path = LIB_PATH.replace(".so", "_trace.so") if trace else LIB_PATH
+    stamp = _STAMP + ("_trace" if trace else "")
+    if not force and os.path.isfile(lib_path) and os.path.isfile(stamp):
+        with open(stamp) as f:
             if f.read().strip() == digest:
-                return LIB_PATH
+                return lib_path
     cmd = [
         nvcc_path(), "-std=c++17", "-O3", "-lineinfo",
         "-gencode", "arch=compute_100a,code=sm_100a",
-        "-Xcompiler", "-fPIC,-O2,-Wall", "-shared",
+        "-Xcompiler", "-fPIC,-O2,-Wall", "-shared", *(["-DMC_TRACE"] if trace else []),
         "-Xptxas", "-v" if verbose else "-O3",
-        "-o", LIB_PATH, os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "audio_decode.cpp"),
+        "-o", lib_path, os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "audio_decode.cpp"),
         "-lcudart",
     ]
     proc = subprocess.run(cmd, capture_output=True, text=True)
@@ -57,10 +61,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed building libmagicodec_b200.so:\n" + proc.stderr[-4000:])
-    with open(_STAMP, "w") as f:
+    with open(stamp, "w") as f:
         f.write(digest)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))

@@ -285,4 +285,31 @@ __global__ void tconv_last_kernel(const __nv_bfloat16* __restrict__ x, int B, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Left padding of the causal conv / transposed-conv inputs: `rows` zero rows of `width` bytes at the head of every
+// item, for up to MC_MAX_CONVS buffers in ONE launch (four cudaMemset2D nodes cost ~2 us each on the batch-1 path).
+// ---------------------------------------------------------------------------------------------
+struct PadList {
+  int n = 0;
+  unsigned char* base[8];
+  long long pitch[8];      // bytes between items
+  int width[8];            // bytes to zero at the head of each item (multiple of 16)
+};
+
+__global__ void __launch_bounds__(256)
+zero_pads_kernel(const PadList pl, int items) {
+  pdl_launch_dependents();
+  pdl_wait();                // the previous pass may still be reading these buffers
+  for (int b = 0; b < pl.n; ++b) {
+    const int chunks = pl.width[b] >> 4;
+    const long long total = static_cast<long long>(items) * chunks;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const long long item = i / chunks;
+      const int c = static_cast<int>(i - item * chunks);
+      *reinterpret_cast<uint4*>(pl.base[b] + item * pl.pitch[b] + (static_cast<long long>(c) << 4)) = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
 }  // namespace mc

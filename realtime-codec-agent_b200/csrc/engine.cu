@@ -27,15 +27,25 @@ struct GemmCall {
   int block_n = 0;  // 0 = choose
   const void* prefetch_ptr = nullptr;   // next GEMM's weights (split-K kernel: L2 prefetch)
   long long prefetch_bytes = 0;
+  // fused RMSNorm (few-rows path, GemmParams): consumer / producer
+  const float* row_stats = nullptr; int row_stats_n = 0;
+  bf16* xb_out = nullptr; const float* xb_gamma = nullptr; float* stat_out = nullptr;
 };
 
-template <int BN>
+void fill_norm_fields(const mc_handle* h, const GemmCall& c, GemmParams& p) {
+  p.row_stats = c.row_stats; p.row_stats_n = c.row_stats_n;
+  p.norm_eps = h->spec.norm_eps; p.inv_norm_dim = c.K > 0 ? 1.0f / (float)c.K : 0.f;   // the consumer's K is the normalised width
+  p.xb_out = c.xb_out; p.xb_gamma = c.xb_gamma; p.stat_out = c.stat_out;
+}
+
+template <int BN, int BM = GEMM_BM, int KPS = 1>
 int launch_gemm_bn(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   const CUtensorMap *ma, *mb;
-  MC_TRY(get_map_2d_bf16(h, c.A, (uint64_t)c.a_k_wrap, (uint64_t)c.a_rows, GEMM_BK, GEMM_BM, &ma));
+  MC_TRY(get_map_2d_bf16(h, c.A, (uint64_t)c.a_k_wrap, (uint64_t)c.a_rows, GEMM_BK, BM, &ma));
   MC_TRY(get_map_2d_bf16(h, c.W, (uint64_t)c.K, (uint64_t)c.N, GEMM_BK, BN, &mb));
   // plain (ungrouped) outputs leave through TMA: bf16 boxes of 64 columns, fp32 boxes of 32
-  const bool tma_out = (c.grp_in == INT_MAX);
+  // 64-row tiles (16 rows per epilogue warp) and fused-norm producers use per-thread stores
+  const bool tma_out = (c.grp_in == INT_MAX) && BM == GEMM_BM && c.xb_out == nullptr;
   const CUtensorMap* mo = ma;
   if (tma_out) {
     const int esize = c.out_mode == OUT_BF16 ? 2 : 4;
@@ -50,13 +60,14 @@ int launch_gemm_bn(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   p.rope_ld = h->spec.max_positions;
   p.rope_cos = c.rope_period > 0 ? h->ptr<float>("rope.cos") : nullptr;
   p.rope_sin = c.rope_period > 0 ? h->ptr<float>("rope.sin") : nullptr;
-  MC_TRY(mc_allow_smem(h, gemm_bf16_sm100_kernel<BN>, GemmCfg<BN>::kSmemBytes));
-  const int m_tiles = (c.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (c.N + BN - 1) / BN;
+  fill_norm_fields(h, c, p);
+  MC_TRY(mc_allow_smem(h, (gemm_bf16_sm100_kernel<BN, BM, KPS>), GemmCfg<BN>::kSmemBytes));
+  const int m_tiles = (c.M + BM - 1) / BM, n_tiles = (c.N + BN - 1) / BN;
   const int grid = std::min(m_tiles * n_tiles, h->num_sms);
   const double valid_rows = c.grp_in == INT_MAX ? (double)c.M : (double)c.M / c.grp_in * c.grp_valid;
   const double out_bytes = valid_rows * c.N * (c.out_mode == OUT_BF16 ? 2.0 : (c.out_mode == OUT_F32 ? 4.0 : 8.0));
   McProfScope prof(h, 0, 2.0 * valid_rows * c.N * c.K, valid_rows * c.a_k_wrap * 2.0 + (double)c.N * c.K * 2.0 + out_bytes, stream);
-  mc_launch(h, gemm_bf16_sm100_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), GemmCfg<BN>::kSmemBytes, stream, *ma, *mb, *mo, p);
+  mc_launch(h, gemm_bf16_sm100_kernel<BN, BM, KPS>, dim3(grid), dim3(GEMM_THREADS), GemmCfg<BN>::kSmemBytes, stream, *ma, *mb, *mo, p);
   MC_LAUNCH_CHECK(h, "gemm_bf16_sm100_kernel");
   return MC_OK;
 }
@@ -125,6 +136,7 @@ int launch_gemm_splitk_s(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   p.rope_cos = c.rope_period > 0 ? h->ptr<float>("rope.cos") : nullptr;
   p.rope_sin = c.rope_period > 0 ? h->ptr<float>("rope.sin") : nullptr;
   if (h->l2_prefetch) { p.prefetch_ptr = c.prefetch_ptr; p.prefetch_bytes = c.prefetch_bytes; }
+  fill_norm_fields(h, c, p);
   auto kernel = gemm_splitk_sm100_kernel<BN, S>;
   MC_TRY(mc_allow_smem(h, kernel, GemmSkCfg<BN>::kSmemBytes));
   const int m_tiles = (c.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (c.N + BN - 1) / BN;
@@ -141,7 +153,12 @@ int launch_gemm_splitk_s(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = h->pdl ? 2 : 1;
-  (void)cudaLaunchKernelEx(&cfg, kernel, *ma, *mb, p);
+  const int nkb = (c.K / GEMM_BK) / S;
+  // k-blocks per barrier round trip: 1.  A CTA's slice is only 2 .. 10 k-blocks and the first MMA should start as soon as
+  // the first k-block has landed; grouping them (measured: Wo 6.3 -> 6.7 us, W2 8.1 -> 8.6 us) delays it.
+  const int kps = 1;
+  (void)nkb;
+  (void)cudaLaunchKernelEx(&cfg, kernel, *ma, *mb, p, kps);
   MC_LAUNCH_CHECK(h, "gemm_splitk_sm100_kernel");
   return MC_OK;
 }
@@ -155,8 +172,12 @@ int launch_gemm_splitk_s(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
 int pick_split_k(const mc_handle* h, const GemmCall& c) {
   if (c.M > 2 * GEMM_BM) return 0;
   const int base = ((c.M + GEMM_BM - 1) / GEMM_BM) * ((c.N + 63) / 64);
-  if (base > 32) return 0;
   const int num_kb = c.K / GEMM_BK;
+  if (base > 32) {
+    // a few more tiles, but a long K (the first transposed conv of the decoder: 40 tiles, K = 2048): two CTAs per SM
+    if (base <= 48 && num_kb >= 32 && num_kb % 4 == 0) return 4;
+    return 0;
+  }
   for (int s = 8; s >= 2; s >>= 1)
     if (num_kb % s == 0 && num_kb / s >= 2 && base * s <= h->num_sms) return s;
   return 0;
@@ -180,7 +201,13 @@ int launch_gemm(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   if (c.rope_period > 0 && c.rope_period + c.rope_offset > h->spec.max_positions)
     return h->fail(MC_ERR_ARG, "gemm: rope period %d exceeds table rows %d", c.rope_period, h->spec.max_positions);
   int bn = c.block_n;
+  if ((c.row_stats || c.xb_out) && c.M > 2 * GEMM_BM) return h->fail(MC_ERR_ARG, "gemm: fused RMSNorm is a few-rows (M <= 256) feature");
+  if (c.xb_out && (c.out_mode == OUT_BF16 || c.N % 64 != 0 || !c.xb_gamma || !c.stat_out))
+    return h->fail(MC_ERR_ARG, "gemm: fused RMSNorm producer needs an fp32 output, N %% 64 == 0, gamma and a stats buffer");
   if (bn >= 1002 && bn <= 1008) return launch_gemm_splitk(h, c, bn - 1000, stream);   // forced (tests / A-B timing)
+  if (bn == 2064) return launch_gemm_bn<64, 64>(h, c, stream);                        // 64-row UMMA tiles
+  if (bn == 3064 && (c.K / GEMM_BK) % 2 == 0) return launch_gemm_bn<64, GEMM_BM, 2>(h, c, stream);   // 2 k-blocks per barrier round trip
+  if (bn == 4064 && (c.K / GEMM_BK) % 4 == 0) return launch_gemm_bn<64, GEMM_BM, 4>(h, c, stream);   // 4
   if (bn == 0 && (h->split_k == 2 || (h->split_k == 1 && h->in_session))) {
     const int S = pick_split_k(h, c);
     if (S >= 2) return launch_gemm_splitk(h, c, S, stream);
@@ -197,6 +224,9 @@ int launch_gemm(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
     else if (c.N >= 256 && m_tiles * ((c.N + 255) / 256) >= h->num_sms) bn = 256;
     else bn = 64;
   }
+  if (bn == 64 && c.block_n == 0 && (c.K / GEMM_BK) % 4 == 0 &&
+      ((c.M + GEMM_BM - 1) / GEMM_BM) * ((c.N + 63) / 64) <= h->num_sms)
+    return launch_gemm_bn<64, GEMM_BM, 4>(h, c, stream);   // one tile per CTA: four k-blocks per barrier round trip (bit-identical)
   switch (bn) {
     case 256: return launch_gemm_bn<256>(h, c, stream);
     case 128: return launch_gemm_bn<128>(h, c, stream);
@@ -260,7 +290,14 @@ struct StackBufs {
   bf16* qkv;  // [M,3d]
   bf16* att;  // [M,d]
   bf16* ffn;  // [M,f]
+  float* stats;  // [M, d/64] per-row partial sums of x^2 (fused RMSNorm on the few-rows path)
 };
+
+// RMSNorm folded into the neighbouring GEMMs (GemmParams: producer / consumer): only on the few-rows path, i.e. under the
+// same switch as the split-K kernels, so that a session and a stateless call in the same mode run identical kernels.
+bool fuse_norm_ok(const mc_handle* h, long long M) {
+  return h->fuse_norm && (h->split_k == 2 || (h->split_k == 1 && h->in_session)) && M <= 2 * GEMM_BM && h->spec.d_model % 64 == 0;
+}
 
 // Runs n_layers blocks over B windows of F frames held in b.x and returns, in *x_out, the residual
 // stream restricted to the LAST keep_rows frames of every window ([B*keep_rows, d]).
@@ -269,17 +306,25 @@ struct StackBufs {
 // needs keys/values for the last R_in = min(F, R_out + window_left) rows, so working backwards from
 // keep_rows each layer gets (R_in, R_out); rows outside are never computed.  Per-row arithmetic is
 // unchanged (same K order, same epilogues), so kept rows are bit-identical to the full pass.
+//
+// fused = true (few-rows path): the caller has already put bf16(x * gamma_norm1[0]) in b.hbuf and the rows' partial sums
+// of squares in b.stats (its last GEMM ran as a "producer"); every norm of the stack then lives in GEMM epilogues — QKV
+// and W1 scale their accumulator rows by rs(row), Wo and W2 emit the next norm's operand — and no rmsnorm kernel is
+// launched.  final_gamma (may be NULL) is the weight of the norm that FOLLOWS the stack: the last W2 emits that
+// operand, returned with its statistics through xb_out / stats_out.
 int run_layers(mc_handle* h, const char* prefix, int n_layers, const StackBufs& b, int B, int F, int keep_rows,
-               float** x_out, cudaStream_t stream) {
+               float** x_out, cudaStream_t stream, bool fused = false, const float* final_gamma = nullptr,
+               bf16** xb_out = nullptr, float** stats_out = nullptr) {
   const mc_spec& s = h->spec;
   const int d = s.d_model, f = s.ffn_dim;
+  const int nst = d / 64;
   std::vector<int> r_in(n_layers), r_out(n_layers);
   {
     int need = std::max(1, std::min(keep_rows, F));
     // One 128-row tile (a batch-1 streaming pass): dropping rows saves nothing — every GEMM is one tile either way —
     // and the row compactions would be three more launches on the latency path.  Per-row results do not depend on
     // which other rows are computed, so this stays bit-identical.
-    if ((long long)B * F <= GEMM_BM) need = F;
+    if (B == 1 && F <= GEMM_BM) need = F;
     for (int l = n_layers - 1; l >= 0; --l) {
       r_out[l] = need;
       need = (need >= F) ? F : std::min(F, need + s.window_left);
@@ -301,8 +346,9 @@ int run_layers(mc_handle* h, const char* prefix, int n_layers, const StackBufs& 
     };
     const int Ri = rows, Ro = std::min(r_out[l], rows);
     const int Mi = B * Ri, Mo = B * Ro;
-    MC_TRY(launch_rmsnorm(h, x, h->ptr<float>(T("norm1")), b.hbuf, Mi, d, INT_MAX, 0, 0, stream));
+    if (!fused) MC_TRY(launch_rmsnorm(h, x, h->ptr<float>(T("norm1")), b.hbuf, Mi, d, INT_MAX, 0, 0, stream));
     GemmCall g{};
+    if (fused) { g.row_stats = b.stats; g.row_stats_n = nst; }
     g.A = b.hbuf; g.a_rows = Mi; g.a_k_wrap = d; g.W = h->ptr<bf16>(T("wqkv")); g.bias = h->ptr<float>(T("bqkv"));
     g.M = Mi; g.N = 3 * d; g.K = d; g.act = ACT_NONE; g.out_mode = OUT_BF16; g.out = b.qkv; g.ldo = 3 * d;
     g.rope_cols = 2 * d; g.rope_period = Ri; g.rope_offset = F - Ri;
@@ -322,9 +368,11 @@ int run_layers(mc_handle* h, const char* prefix, int n_layers, const StackBufs& 
     o.A = b.att; o.a_rows = Mo; o.a_k_wrap = d; o.W = h->ptr<bf16>(T("wo")); o.bias = h->ptr<float>(T("bo"));
     o.M = Mo; o.N = d; o.K = d; o.act = ACT_NONE; o.out_mode = OUT_F32_RESIDUAL; o.out = x; o.ldo = d;
     o.prefetch_ptr = h->ptr<bf16>(T("w1")); o.prefetch_bytes = (long long)f * d * 2;
+    if (fused) { o.xb_out = b.hbuf; o.xb_gamma = h->ptr<float>(T("norm2")); o.stat_out = b.stats; }
     MC_TRY(launch_gemm(h, o, stream));
-    MC_TRY(launch_rmsnorm(h, x, h->ptr<float>(T("norm2")), b.hbuf, Mo, d, INT_MAX, 0, 0, stream));
+    if (!fused) MC_TRY(launch_rmsnorm(h, x, h->ptr<float>(T("norm2")), b.hbuf, Mo, d, INT_MAX, 0, 0, stream));
     GemmCall u{};
+    if (fused) { u.row_stats = b.stats; u.row_stats_n = nst; }
     u.A = b.hbuf; u.a_rows = Mo; u.a_k_wrap = d; u.W = h->ptr<bf16>(T("w1")); u.bias = h->ptr<float>(T("b1"));
     u.M = Mo; u.N = f; u.K = d; u.act = ACT_GELU_TANH; u.out_mode = OUT_BF16; u.out = b.ffn; u.ldo = f;
     u.prefetch_ptr = h->ptr<bf16>(T("w2")); u.prefetch_bytes = (long long)d * f * 2;
@@ -336,9 +384,23 @@ int run_layers(mc_handle* h, const char* prefix, int n_layers, const StackBufs& 
       snprintf(name, sizeof(name), "%s.layers.%d.wqkv", prefix, l + 1);
       w.prefetch_ptr = h->ptr<bf16>(name); w.prefetch_bytes = (long long)3 * d * d * 2;
     }
+    if (fused) {
+      const float* next_gamma = final_gamma;
+      if (l + 1 < n_layers) {
+        snprintf(name, sizeof(name), "%s.layers.%d.norm1", prefix, l + 1);
+        next_gamma = h->ptr<float>(name);
+      }
+      if (next_gamma) { w.xb_out = b.hbuf; w.xb_gamma = next_gamma; w.stat_out = b.stats; }
+    }
     MC_TRY(launch_gemm(h, w, stream));
   }
-  if (rows > keep_rows) {  // no layers (or window_left = 0 corner cases): compact at the end
+  bf16* xb = b.hbuf;
+  float* st = b.stats;
+  if (rows > keep_rows && B == 1) {
+    x += (size_t)(rows - keep_rows) * d;   // one window: its last rows are already contiguous — no copy
+    xb += (size_t)(rows - keep_rows) * d;
+    st += (size_t)(rows - keep_rows) * nst;
+  } else if (rows > keep_rows) {  // single-tile passes keep every row through the layers: compact at the end
     const int Ro = keep_rows;
     const long long items = (long long)B * Ro * (d / 4);
     mc_launch(h, compact_rows_kernel, dim3(ew_grid(h, items, 256)), dim3(256), 0, stream, reinterpret_cast<const float4*>(x),
@@ -346,15 +408,20 @@ int run_layers(mc_handle* h, const char* prefix, int n_layers, const StackBufs& 
     MC_LAUNCH_CHECK(h, "compact_rows_kernel");
     std::swap(x, xalt);
   }
+  if (fused && rows > keep_rows && B != 1) return h->fail(MC_ERR_STATE, "run_layers: fused norms with a trailing compaction");
   *x_out = x;
+  if (xb_out) *xb_out = xb;
+  if (stats_out) *stats_out = st;
   return MC_OK;
 }
 
 StackBufs carve_stack(Carver& cv, uint8_t* base, int M, int d, int f, bool dry) {
   StackBufs b{};
   size_t ox = cv.take((size_t)M * d * 4), ox2 = cv.take((size_t)M * d * 4), oh = cv.take((size_t)M * d * 2),
-         oq = cv.take((size_t)M * 3 * d * 2), oa = cv.take((size_t)M * d * 2), of = cv.take((size_t)M * f * 2);
+         oq = cv.take((size_t)M * 3 * d * 2), oa = cv.take((size_t)M * d * 2), of = cv.take((size_t)M * f * 2),
+         os = cv.take((size_t)M * (d / 64 + 1) * 4);
   if (!dry) {
+    b.stats = reinterpret_cast<float*>(base + os);
     b.x = reinterpret_cast<float*>(base + ox);
     b.x2 = reinterpret_cast<float*>(base + ox2);
     b.hbuf = reinterpret_cast<bf16*>(base + oh);
@@ -391,15 +458,28 @@ ConvPlan plan_conv(const mc_spec& s, Carver& cv, int Bc, int Tc_padded) {
 }
 
 int run_conv_stack(mc_handle* h, const ConvPlan& cp, uint8_t* base, const float* wav, int64_t ld, int Tvalid,
-                   float* x_out, int64_t x_item_stride, cudaStream_t stream) {
+                   float* x_out, int64_t x_item_stride, cudaStream_t stream, bf16* xb_out = nullptr,
+                   const float* xb_gamma = nullptr, float* stat_out = nullptr) {
   const mc_spec& s = h->spec;
   const int n = s.n_convs, d = s.d_model, B = cp.B;
   const std::vector<int>& Tl = cp.Tl;
   const int* Cl = s.conv_channels;
-  for (int i = 0; i + 1 < n; ++i) {  // zero the left padding of every conv input
-    const int pad = s.conv_strides[i + 1];
-    const size_t pitch = (size_t)(pad + Tl[i]) * Cl[i] * 2;
-    MC_CUDA(h, cudaMemset2DAsync(base + cp.off[i], pitch, 0, (size_t)pad * Cl[i] * 2, B, stream));
+  {  // zero the left padding of every conv input (one launch)
+    PadList pl;
+    long long work = 0;
+    for (int i = 0; i + 1 < n; ++i) {
+      const int pad = s.conv_strides[i + 1];
+      pl.base[pl.n] = base + cp.off[i];
+      pl.pitch[pl.n] = (long long)(pad + Tl[i]) * Cl[i] * 2;
+      pl.width[pl.n] = pad * Cl[i] * 2;
+      if (pl.width[pl.n] % 16 != 0 || pl.pitch[pl.n] % 16 != 0) return h->fail(MC_ERR_ARG, "conv %d: padding is not 16-byte granular", i + 1);
+      work = std::max(work, (long long)B * (pl.width[pl.n] >> 4));
+      ++pl.n;
+    }
+    if (pl.n > 0) {
+      mc_launch(h, zero_pads_kernel, dim3(ew_grid(h, work, 256)), dim3(256), 0, stream, pl, B);
+      MC_LAUNCH_CHECK(h, "zero_pads_kernel");
+    }
   }
   {
     const int s0 = s.conv_strides[0], C0 = Cl[0];
@@ -438,6 +518,7 @@ int run_conv_stack(mc_handle* h, const ConvPlan& cp, uint8_t* base, const float*
     } else {
       g.act = ACT_NONE; g.out_mode = OUT_F32; g.out = x_out; g.ldo = d;
       g.grp_stride = x_item_stride; g.grp_off = 0;
+      g.xb_out = xb_out; g.xb_gamma = xb_gamma; g.stat_out = stat_out;   // fused RMSNorm: first producer of the encoder stack
     }
     MC_TRY(launch_gemm(h, g, stream));
   }
@@ -483,6 +564,8 @@ int encode_impl(mc_handle* h, const float* wav, int64_t ld, int B, int T, int ke
   const long long span_frames = span_samples / hop;
   const bool shared = h->shared_stem && B >= 2 && ld > 0 && ld < T && ld % hop == 0 && T % hop == 0 && F > pre &&
                       span_samples <= INT_MAX && span_frames + (long long)pre * B < (long long)B * F / 2;
+  // RMSNorms inside GEMM epilogues on the few-rows path (the keep < F case with several windows compacts rows at the end)
+  const bool fused = fuse_norm_ok(h, Mll + B) && !shared && s.enc_layers > 0;   // + B: the last conv GEMM carries one junk row per window
 
   // ---- carve workspace (sizes first, then pointers)
   Carver cv;
@@ -516,16 +599,22 @@ int encode_impl(mc_handle* h, const float* wav, int64_t ld, int B, int T, int ke
               reinterpret_cast<float4*>(sb.x), B, F, pre, (int)(ld / hop), d / 4);
     MC_LAUNCH_CHECK(h, "gather_stem_kernel");
   } else {
-    MC_TRY(run_conv_stack(h, cp_full, base, wav, ld, T, sb.x, (int64_t)F * d, stream));
+    if (fused)
+      MC_TRY(run_conv_stack(h, cp_full, base, wav, ld, T, sb.x, (int64_t)F * d, stream, sb.hbuf, h->ptr<float>("enc.layers.0.norm1"), sb.stats));
+    else
+      MC_TRY(run_conv_stack(h, cp_full, base, wav, ld, T, sb.x, (int64_t)F * d, stream));
   }
   // ---- transformer (only the rows the kept frames depend on, unless the full latents are requested)
   const int keep_rows = z_e_out ? F : keep;
   float* xk = nullptr;
-  MC_TRY(run_layers(h, "enc", s.enc_layers, sb, B, F, keep_rows, &xk, stream));
+  bf16* xbk = sb.hbuf;
+  float* stk = nullptr;
+  MC_TRY(run_layers(h, "enc", s.enc_layers, sb, B, F, keep_rows, &xk, stream, fused, fused ? h->ptr<float>("enc.norm_f") : nullptr, &xbk, &stk));
   const int Mk = B * keep_rows;
-  MC_TRY(launch_rmsnorm(h, xk, h->ptr<float>("enc.norm_f"), sb.hbuf, Mk, d, INT_MAX, 0, 0, stream));
+  if (!fused) MC_TRY(launch_rmsnorm(h, xk, h->ptr<float>("enc.norm_f"), sb.hbuf, Mk, d, INT_MAX, 0, 0, stream));
   GemmCall pj{};
-  pj.A = sb.hbuf; pj.a_rows = Mk; pj.a_k_wrap = d; pj.W = h->ptr<bf16>("enc.proj.w"); pj.bias = h->ptr<float>("enc.proj.b");
+  if (fused) { pj.row_stats = stk; pj.row_stats_n = d / 64; }
+  pj.A = fused ? xbk : sb.hbuf; pj.a_rows = Mk; pj.a_k_wrap = d; pj.W = h->ptr<bf16>("enc.proj.w"); pj.bias = h->ptr<float>("enc.proj.b");
   pj.M = Mk; pj.N = dq; pj.K = d; pj.act = ACT_NONE; pj.out_mode = OUT_F32; pj.out = z_e; pj.ldo = dq;
   MC_TRY(launch_gemm(h, pj, stream));
   if (z_e_out) MC_CUDA(h, cudaMemcpyAsync(z_e_out, z_e, (size_t)M * dq * 4, cudaMemcpyDeviceToDevice, stream));
@@ -585,13 +674,25 @@ int decode_impl(mc_handle* h, const int64_t* codes, const float* z_q, int B, int
   GemmCall ip{};
   ip.A = a0; ip.a_rows = M; ip.a_k_wrap = 64; ip.W = h->ptr<bf16>("dec.in_proj.w"); ip.bias = h->ptr<float>("dec.in_proj.b");
   ip.M = M; ip.N = d; ip.K = 64; ip.act = ACT_NONE; ip.out_mode = OUT_F32; ip.out = sb.x; ip.ldo = d;
+  const bool fused = fuse_norm_ok(h, Mll) && s.dec_layers > 0;
+  if (fused) { ip.xb_out = sb.hbuf; ip.xb_gamma = h->ptr<float>("dec.layers.0.norm1"); ip.stat_out = sb.stats; }
   MC_TRY(launch_gemm(h, ip, stream));
   float* xk = nullptr;
-  MC_TRY(run_layers(h, "dec", s.dec_layers, sb, B, F, Rk, &xk, stream));
+  MC_TRY(run_layers(h, "dec", s.dec_layers, sb, B, F, Rk, &xk, stream, fused));
 
-  for (int i = 0; i < n; ++i) {  // zero row 0 (left pad) of every transposed-conv input
-    const size_t pitch = (size_t)(1 + Tin[i]) * dch[i] * 2;
-    MC_CUDA(h, cudaMemset2DAsync(base + tb_off[i], pitch, 0, (size_t)dch[i] * 2, B, stream));
+  {  // zero row 0 (left pad) of every transposed-conv input (one launch)
+    PadList pl;
+    long long work = 0;
+    for (int i = 0; i < n; ++i) {
+      pl.base[pl.n] = base + tb_off[i];
+      pl.pitch[pl.n] = (long long)(1 + Tin[i]) * dch[i] * 2;
+      pl.width[pl.n] = dch[i] * 2;
+      if (pl.width[pl.n] % 16 != 0) return h->fail(MC_ERR_ARG, "tconv %d: %d channels are not 16-byte granular", i, dch[i]);
+      work = std::max(work, (long long)B * (pl.width[pl.n] >> 4));
+      ++pl.n;
+    }
+    mc_launch(h, zero_pads_kernel, dim3(ew_grid(h, work, 256)), dim3(256), 0, stream, pl, B);
+    MC_LAUNCH_CHECK(h, "zero_pads_kernel");
   }
   MC_TRY(launch_rmsnorm(h, xk, h->ptr<float>("dec.norm_f"), reinterpret_cast<bf16*>(base + tb_off[0]), B * Rk, d, Rk,
                         (int64_t)(1 + Rk) * d, d, stream));
@@ -832,6 +933,25 @@ int mc_op_resample(mc_handle* h, const float* in, int64_t in_ld, int32_t channel
   return MC_OK;
 }
 
+/* Timeline build only (-DMC_TRACE): point the kernels' wait-time log at dev_buf (4 x uint64 per record: grid<<32|block,
+ * block size, timer before / after griddepcontrol.wait); dev_buf = NULL stops logging.  Returns the records logged so far. */
+int64_t mc_debug_trace(mc_handle* h, void* dev_buf, int64_t capacity_records) {
+  if (!h) return MC_ERR_ARG;
+#ifdef MC_TRACE
+  unsigned int n = 0, zero = 0, cap = (unsigned int)capacity_records;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_mc_trace_n, sizeof(n));
+  unsigned long long* ptr = reinterpret_cast<unsigned long long*>(dev_buf);
+  cudaMemcpyToSymbol(g_mc_trace, &ptr, sizeof(ptr));
+  cudaMemcpyToSymbol(g_mc_trace_cap, &cap, sizeof(cap));
+  cudaMemcpyToSymbol(g_mc_trace_n, &zero, sizeof(zero));
+  return (int64_t)n;
+#else
+  (void)dev_buf; (void)capacity_records;
+  return h->fail(MC_ERR_STATE, "mc_debug_trace: the library was built without -DMC_TRACE");
+#endif
+}
+
 int64_t mc_launch_count(const mc_handle* h) { return h ? h->launches : 0; }
 
 int mc_profile_begin(mc_handle* h) {
@@ -868,6 +988,7 @@ int mc_set_option(mc_handle* h, const char* key, int32_t value) {
   else if (k == "attn_p_tmem") h->attn_p_tmem = value != 0;
   else if (k == "debug_repeat") h->debug_repeat = value;   // mc_op_* launch their kernel `value` times back to back (timing tools)
   else if (k == "l2_prefetch") { h->l2_prefetch = value != 0; h->tensor_gen++; }
+  else if (k == "fuse_norm") { h->fuse_norm = value != 0; h->tensor_gen++; }
   else if (k == "small_m_split_k") {   // 0 never, 1 streaming sessions only (default), 2 every GEMM of <= 256 rows
     if (value < 0 || value > 2) return h->fail(MC_ERR_ARG, "mc_set_option: small_m_split_k is 0, 1 or 2");
     h->split_k = value;

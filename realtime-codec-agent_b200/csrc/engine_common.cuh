@@ -69,6 +69,7 @@ struct mc_handle {
   int split_k = 1;
   bool in_session = false;
   int debug_repeat = 1;
+  bool fuse_norm = true;      // few-rows path: RMSNorms live in the epilogues of the GEMMs around them (no rmsnorm launches)
   bool l2_prefetch = true;    // split-K GEMMs pull the next GEMM's weights into L2 while they run
   bool pdl = true;            // programmatic dependent launch between consecutive kernels of a pass
   bool shared_stem = true;  // overlapping hop-aligned windows share one pass of the conv stack (exact)
@@ -196,8 +197,8 @@ struct Carver {
 // 2-D tiled, 128B-swizzled tensor map over a row-major [dim1, dim0] array of `esize`-byte elements
 // with `row_stride_bytes` between rows (esize 2 = bf16, 4 = fp32).
 inline int get_map_2d(mc_handle* h, const void* base, int esize, uint64_t dim0, uint64_t dim1, uint64_t row_stride_bytes,
-                      uint32_t box0, uint32_t box1, const CUtensorMap** out) {
-  auto key = std::make_tuple(base, dim0, dim1, row_stride_bytes, (uint32_t)(box0 | (esize << 16)), box1);
+                      uint32_t box0, uint32_t box1, const CUtensorMap** out, int swizzle_bytes = 128) {
+  auto key = std::make_tuple(base, dim0, dim1, row_stride_bytes, (uint32_t)(box0 | (esize << 16) | (swizzle_bytes << 20)), box1);
   auto it = h->maps.find(key);
   if (it != h->maps.end()) {
     *out = &it->second;
@@ -205,7 +206,7 @@ inline int get_map_2d(mc_handle* h, const void* base, int esize, uint64_t dim0, 
   }
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return h->fail(MC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || row_stride_bytes % 16 != 0 || box0 * esize > 128)
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || row_stride_bytes % 16 != 0 || box0 * esize > (uint32_t)swizzle_bytes)
     return h->fail(MC_ERR_ARG, "TMA operand misaligned (base %p, row stride %llu B, box %u x %d B)", base,
                    (unsigned long long)row_stride_bytes, box0, esize);
   CUtensorMap m;
@@ -215,7 +216,8 @@ inline int get_map_2d(mc_handle* h, const void* base, int esize, uint64_t dim0, 
   cuuint32_t estride[2] = {1, 1};
   CUresult r = enc(&m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return h->fail(MC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) dims %llu x %llu box %u x %u esize %d", (int)r,
                    (unsigned long long)dim0, (unsigned long long)dim1, box0, box1, esize);
@@ -224,7 +226,7 @@ inline int get_map_2d(mc_handle* h, const void* base, int esize, uint64_t dim0, 
   return MC_OK;
 }
 inline int get_map_2d_bf16(mc_handle* h, const void* base, uint64_t dim0, uint64_t dim1, uint32_t box0, uint32_t box1,
-                           const CUtensorMap** out) {
-  return get_map_2d(h, base, 2, dim0, dim1, dim0 * 2, box0, box1, out);
+                           const CUtensorMap** out, int swizzle_bytes = 128) {
+  return get_map_2d(h, base, 2, dim0, dim1, dim0 * 2, box0, box1, out, swizzle_bytes);
 }
 }  // namespace mc_internal

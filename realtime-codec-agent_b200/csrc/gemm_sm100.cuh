@@ -48,7 +48,25 @@ struct GemmParams {
   // split-K kernel only: the NEXT GEMM's weights, pulled into L2 while this kernel runs (they do not depend on it)
   const void* prefetch_ptr = nullptr;
   long long prefetch_bytes = 0;
+  // RMSNorm folded into the GEMMs around it (few-rows path; single-CTA generic epilogue and split-K kernel):
+  //   consumer  y = acc * rs(row) + bias,  rs = rsqrt(sum_c row_stats[row][c] / norm_dim + eps)   (A = bf16(x * gamma))
+  //   producer  (fp32 outputs) also emits xb = bf16(x_new * gamma) as dense rows [rows, N] and, per row and per
+  //             64-column chunk, the sum of x_new^2 -> stat_out[row][N / 64]
+  const float* row_stats = nullptr;
+  int row_stats_n = 0;
+  float norm_eps = 0.f, inv_norm_dim = 0.f;
+  __nv_bfloat16* xb_out = nullptr;
+  const float* xb_gamma = nullptr;
+  float* stat_out = nullptr;
 };
+
+// rs of one row from its per-chunk partial sums (fixed order)
+__device__ __forceinline__ float row_rs(const GemmParams& p, int row) {
+  const float* st = p.row_stats + static_cast<long long>(row) * p.row_stats_n;
+  float s = 0.f;
+  for (int c = 0; c < p.row_stats_n; ++c) s += __ldg(st + c);
+  return rsqrtf(fmaf(s, p.inv_norm_dim, p.norm_eps));
+}
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
@@ -108,17 +126,18 @@ __device__ __forceinline__ void epi_load_bias(const GemmParams& p, int n0, float
 // Everything that needs global memory (bias of the first chunk, RoPE angles of the row) is requested
 // BEFORE waiting for the accumulator, and each later chunk's bias is requested one chunk ahead, so no
 // L2 round trip sits between tcgen05.ld and the store (L1 is ~0 KB here: smem takes the whole 228 KB).
-template <int BN>
+template <int BN, int RPW = 32>   // RPW: accumulator rows per epilogue warp (32 for 128-row tiles, 16 for 64-row tiles: lanes 0..15)
 __device__ __forceinline__ void gemm_epilogue_slab(const GemmParams& p, const CUtensorMap* map_out_p, uint32_t tmem_acc,
                                                    int row_base, int n_base, int q, int lane, uint8_t* my_bufs,
                                                    EpiRegs& st, uint64_t* ready_bar, uint32_t ready_parity) {
-  const int g = row_base + q * 32 + lane;  // A row handled by this thread
+  const int g = row_base + q * RPW + (lane < RPW ? lane : 0);  // A row handled by this thread
   const int grp = g / p.grp_in;
   const int r = g - grp * p.grp_in;
-  const bool row_ok = (g < p.M) && (r < p.grp_valid);
+  const bool row_ok = (lane < RPW) && (g < p.M) && (r < p.grp_valid);
   const long long obase = static_cast<long long>(grp) * p.grp_stride + p.grp_off + static_cast<long long>(r) * p.ldo;
   const bool has_bias = p.bias != nullptr;
   if (has_bias) epi_load_bias<BN>(p, n_base, st.bias);
+  const float rs = (p.row_stats != nullptr && g < p.M) ? row_rs(p, g) : 1.0f;
   if (p.rope_period > 0) {
     const int pos = p.rope_offset + r % p.rope_period;
     if (pos != st.rope_pos) {
@@ -148,6 +167,10 @@ __device__ __forceinline__ void gemm_epilogue_slab(const GemmParams& p, const CU
     for (int j = 0; j < 32; ++j) {
       v[j] = __uint_as_float(raw0[j]);
       v[32 + j] = __uint_as_float(raw1[j]);
+    }
+    if (p.row_stats != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) v[j] *= rs;
     }
     if (has_bias) {
 #pragma unroll
@@ -232,7 +255,45 @@ __device__ __forceinline__ void gemm_epilogue_slab(const GemmParams& p, const CU
         }
       } else {
         float* o = reinterpret_cast<float*>(p.out) + obase + n0;
-        if (p.out_mode == OUT_F32_RESIDUAL) {
+        if (p.xb_out != nullptr) {
+          // producer of a fused RMSNorm: x_new (fp32) + bf16(x_new * gamma) + this chunk's sum of squares.  All loads
+          // first (gamma, old residual): interleaved with the stores they would serialise on one L2 round trip each.
+          const long long orow = (p.grp_in == INT_MAX) ? g : static_cast<long long>(grp) * p.grp_valid + r;
+          __nv_bfloat16* xb = p.xb_out + orow * p.N + n0;
+          float gam[64];
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            float4 ga = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + j < p.N) ga = __ldg(reinterpret_cast<const float4*>(p.xb_gamma + n0 + j));
+            gam[j] = ga.x; gam[j + 1] = ga.y; gam[j + 2] = ga.z; gam[j + 3] = ga.w;
+          }
+          if (p.out_mode == OUT_F32_RESIDUAL) {
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+              if (n0 + j < p.N) {
+                const float4 a = *reinterpret_cast<const float4*>(o + j);
+                v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
+              }
+            }
+          }
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < 64; j += 8) {
+            if (n0 + j < p.N) {
+              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              *reinterpret_cast<float4*>(o + j + 4) = make_float4(v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) ss = fmaf(v[j + e], v[j + e], ss);
+              uint4 w;
+              w.x = pack_bf16x2(v[j] * gam[j], v[j + 1] * gam[j + 1]);
+              w.y = pack_bf16x2(v[j + 2] * gam[j + 2], v[j + 3] * gam[j + 3]);
+              w.z = pack_bf16x2(v[j + 4] * gam[j + 4], v[j + 5] * gam[j + 5]);
+              w.w = pack_bf16x2(v[j + 6] * gam[j + 6], v[j + 7] * gam[j + 7]);
+              *reinterpret_cast<uint4*>(xb + j) = w;
+            }
+          }
+          p.stat_out[orow * ((p.N + 63) / 64) + (n0 >> 6)] = ss;
+        } else if (p.out_mode == OUT_F32_RESIDUAL) {
 #pragma unroll
           for (int j = 0; j < 64; j += 4) {
             if (n0 + j < p.N) {
@@ -449,27 +510,40 @@ __device__ __forceinline__ void gemm_epilogue_slab_fast(const GemmParams& p, con
   }
 }
 
-template <int BN>
+// BM = 64: 64-row UMMA tiles for few-rows GEMMs.  A tcgen05.mma streams its A rows at one row per clock (measured: 128
+// cycles per M = 128 dispatch whatever N, in 128-byte- or 32-byte-swizzled layout; profiles/r02_small_gemm_chain.log), so
+// a 100-row GEMM as 2 x 64 rows on twice the CTAs halves the K loop; the K order per output element is unchanged.  The
+// 64 accumulator rows sit in TMEM lanes 32q .. 32q+15 (q = 0..3): warp q drains rows 16q .. 16q+15 with lanes 0..15.
+//
+// KPS = 64-wide k-blocks per pipeline stage (per full/empty barrier round trip).  With small tiles the loop is not bound
+// by the tensor pipe or by operand traffic but by the issuing thread's own round trip (mbarrier try_wait, fence, four
+// tcgen05.mma, tcgen05.commit: ~550 cycles per k-block whatever M, N or the smem layout — tools/diag_small_gemm.py);
+// KPS > 1 puts several k-blocks behind ONE wait and ONE commit.
+template <int BN, int BM = GEMM_BM, int KPS = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
+  constexpr int kStagesK = Cfg::kStages / KPS;                 // pipeline depth in units of KPS k-blocks
+  constexpr int kStageBytesK = Cfg::kStageBytes * KPS;
+  static_assert(Cfg::kStages % KPS == 0 && kStagesK >= 2, "stage grouping");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_base = smem + Cfg::kStages * Cfg::kStageBytes;   // 1024-aligned: stage sizes are multiples of 1024
   uint8_t* bar_base = epi_base + Cfg::kEpiBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;                // (barrier slots sized for KPS = 1; kStagesK of them used)
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int m_tiles = (p.M + BM - 1) / BM;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = p.K / GEMM_BK;
+  constexpr uint32_t kTxBytes = (BM * GEMM_BK * 2 + Cfg::kStageBytesB) * KPS;
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -477,7 +551,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     if (p.tma_store) tma_prefetch_desc(&map_out);
   }
   if (warp == 5 && lane == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < kStagesK; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -505,24 +579,27 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; kb += KPS) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kStageBytesA;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          const int k_elem = kb * GEMM_BK;
-          const int row_off = k_elem / p.a_k_wrap;
-          const int a_k = k_elem - row_off * p.a_k_wrap;
-          tma_load_2d(sa, &map_a, &full_bar[stage], a_k, m_blk * GEMM_BM + row_off);
-          tma_load_2d(sb, &map_b, &full_bar[stage], k_elem, n_blk * BN);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          mbar_arrive_expect_tx(&full_bar[stage], kTxBytes);
+#pragma unroll
+          for (int j = 0; j < KPS; ++j) {
+            uint8_t* sa = smem + stage * kStageBytesK + j * Cfg::kStageBytes;
+            uint8_t* sb = sa + Cfg::kStageBytesA;
+            const int k_elem = (kb + j) * GEMM_BK;
+            const int row_off = k_elem / p.a_k_wrap;
+            const int a_k = k_elem - row_off * p.a_k_wrap;
+            tma_load_2d(sa, &map_a, &full_bar[stage], a_k, m_blk * BM + row_off);
+            tma_load_2d(sb, &map_b, &full_bar[stage], k_elem, n_blk * BN);
+          }
+          if (++stage == kStagesK) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 5) {
     // -------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -532,20 +609,23 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; kb += KPS) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kStageBytesA;
-          const uint64_t adesc = umma_smem_desc_sw128(sa, 1024, 16);
-          const uint64_t bdesc = umma_smem_desc_sw128(sb, 1024, 16);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // +32 bytes per K=16 step inside the 128-byte swizzled row (encoded >>4 -> +2)
-            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int j = 0; j < KPS; ++j) {
+            const uint32_t sa = smem_u32(smem + stage * kStageBytesK + j * Cfg::kStageBytes);
+            const uint32_t sb = sa + Cfg::kStageBytesA;
+            const uint64_t adesc = umma_smem_desc_sw128(sa, 1024, 16);
+            const uint64_t bdesc = umma_smem_desc_sw128(sb, 1024, 16);
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              // +32 bytes per K=16 step inside the 128-byte swizzled row (encoded >>4 -> +2)
+              umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | j | k) != 0);
+            }
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          umma_commit(&empty_bar[stage]);  // smem slots reusable once these MMAs retire
+          if (++stage == kStagesK) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);      // accumulator complete -> epilogue
       }
@@ -560,8 +640,8 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      gemm_epilogue_slab<BN>(p, &map_out, tmem_base + acc * BN, m_blk * GEMM_BM, n_blk * BN, q, lane, my_bufs, st,
-                             &tmem_full[acc], acc_phase);
+      gemm_epilogue_slab<BN, BM / 4>(p, &map_out, tmem_base + acc * BN, m_blk * BM, n_blk * BN, q, lane, my_bufs, st,
+                                     &tmem_full[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);

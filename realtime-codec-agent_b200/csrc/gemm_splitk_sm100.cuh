@@ -7,10 +7,11 @@
 // tile: CTA r multiplies K-slice r into its own TMEM accumulator, spills the 128 x BN fp32 partial to its shared
 // memory, and after one cluster barrier every CTA reduces 128/S rows of the tile over DISTRIBUTED shared memory in the
 // fixed order r = 0..S-1 (bit-reproducible), applies the epilogue (bias / tanh-GELU / RoPE / residual / conv group
-// remap) and stores.  N/64 x S CTAs of 97 KB shared memory each: two fit on an SM, so with programmatic dependent
-// launch the NEXT GEMM's CTAs are already resident while this one finishes — and because weights do not depend on the
-// predecessor, their TMA loads are issued BEFORE griddepcontrol.wait: the weight stream of GEMM i+1 overlaps the tail
-// of GEMM i.
+// remap) and stores.  Because weights do not depend on the predecessor kernel, their TMA loads are issued BEFORE
+// griddepcontrol.wait (programmatic dependent launch): the weight stream of GEMM i+1 overlaps the tail of GEMM i, and
+// each GEMM also pulls the NEXT GEMM's weight matrix into L2 (cp.async.bulk.prefetch).  `kps` 64-wide k-blocks share one
+// full / empty barrier pair: at these tile sizes the loop is bound by the issuing thread's wait -> mma -> commit round
+// trip, not by the tensor pipe (gemm_sm100.cuh, KPS).
 //
 // The K order of the summation differs from the single-accumulator kernels (S partial sums added in fp32), so a window
 // encoded alone can differ from the same window inside a large batch in the last bit of a latent (and so in a
@@ -23,7 +24,8 @@ namespace mc {
 
 template <int BN>
 struct GemmSkCfg {
-  static constexpr int kStages = 4;
+  static constexpr int kStages = 4;     // 97 KB: two CTAs per SM, so a dependent GEMM's CTAs can be resident (prologue done, weights
+                                        // in flight) while the predecessor still runs; 8 stages / one CTA per SM measured 2x slower
   static constexpr int kStageBytesA = GEMM_BM * GEMM_BK * 2;
   static constexpr int kStageBytesB = BN * GEMM_BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
@@ -43,7 +45,8 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cluster_addr) {
 
 template <int BN, int S>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
-gemm_splitk_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+gemm_splitk_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p,
+                         const int kps /* k-blocks per barrier round trip: 1, 2 or 4; divides the CTA's k-blocks */) {
   using Cfg = GemmSkCfg<BN>;
   static_assert(BN % 64 == 0 && (S == 2 || S == 4 || S == 8), "tile / split shapes");
   extern __shared__ uint8_t smem_raw[];
@@ -63,6 +66,8 @@ gemm_splitk_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   const int m_blk = cid / n_tiles, n_blk = cid % n_tiles;
   const int nkb = (p.K / GEMM_BK) / S;                       // k-blocks per CTA (launcher guarantees divisibility, >= 1)
   const int kb0 = rank * nkb;
+  const int n_groups = nkb / kps;                            // barrier round trips of this CTA
+  const int slots = Cfg::kStages / kps;                      // groups resident in the ring
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -96,55 +101,109 @@ gemm_splitk_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // Reduce-phase identity of the epilogue threads (warps 0-3): CTA `rank` finishes rows [rank*128/S, (rank+1)*128/S) of
+  // the tile, S threads per row, each owning kHalf columns in both halves of the 64-wide block (RoPE pairs j, j+32).
+  static_assert(BN == 64, "one 64-column block per tile");
+  constexpr int kRows = GEMM_BM / S;
+  constexpr int kHalf = 32 / S;
+  const int e_row = rank * kRows + (threadIdx.x & 127) / S;
+  const int e_c0 = ((threadIdx.x & 127) % S) * kHalf;
+  const int e_g = m_blk * GEMM_BM + e_row;                    // A row
+  const int e_grp = e_g / p.grp_in;
+  const int e_r = e_g - e_grp * p.grp_in;
+  const bool e_live = e_g < p.M && e_r < p.grp_valid;
+  const long long e_obase = static_cast<long long>(e_grp) * p.grp_stride + p.grp_off + static_cast<long long>(e_r) * p.ldo;
+  const long long e_orow = (p.grp_in == INT_MAX) ? e_g : static_cast<long long>(e_grp) * p.grp_valid + e_r;
+  float e_bias[2][kHalf], e_gamma[2][kHalf], e_xold[2][kHalf], e_cos[kHalf], e_sin[kHalf], e_rs = 1.0f;
+
   if (warp == 4) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      const int n_pre = nkb < Cfg::kStages ? nkb : Cfg::kStages;
+      const uint32_t tx = static_cast<uint32_t>(Cfg::kStageBytes) * kps;
+      const int n_pre = n_groups < slots ? n_groups : slots;
       // weights first: they do not depend on the predecessor kernel, so their loads run under its tail
-      for (int i = 0; i < n_pre; ++i) {
-        uint8_t* sb = smem + i * Cfg::kStageBytes + Cfg::kStageBytesA;
-        mbar_arrive_expect_tx(&full_bar[i], Cfg::kStageBytes);
-        tma_load_2d(sb, &map_b, &full_bar[i], (kb0 + i) * GEMM_BK, n_blk * BN);
+      for (int g = 0; g < n_pre; ++g) {
+        mbar_arrive_expect_tx(&full_bar[g], tx);
+        for (int j = 0; j < kps; ++j) {
+          uint8_t* sb = smem + (g * kps + j) * Cfg::kStageBytes + Cfg::kStageBytesA;
+          tma_load_2d(sb, &map_b, &full_bar[g], (kb0 + g * kps + j) * GEMM_BK, n_blk * BN);
+        }
       }
       pdl_wait();                                             // activations are the predecessor's output
-      for (int i = 0; i < n_pre; ++i) {
-        const int k_elem = (kb0 + i) * GEMM_BK;
-        const int row_off = k_elem / p.a_k_wrap;
-        tma_load_2d(smem + i * Cfg::kStageBytes, &map_a, &full_bar[i], k_elem - row_off * p.a_k_wrap, m_blk * GEMM_BM + row_off);
+      for (int g = 0; g < n_pre; ++g) {
+        for (int j = 0; j < kps; ++j) {
+          const int k_elem = (kb0 + g * kps + j) * GEMM_BK;
+          const int row_off = k_elem / p.a_k_wrap;
+          tma_load_2d(smem + (g * kps + j) * Cfg::kStageBytes, &map_a, &full_bar[g], k_elem - row_off * p.a_k_wrap,
+                      m_blk * GEMM_BM + row_off);
+        }
       }
-      for (int i = n_pre; i < nkb; ++i) {
-        const int stage = i % Cfg::kStages;
-        const uint32_t phase = (i / Cfg::kStages) & 1;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * Cfg::kStageBytes;
-        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-        const int k_elem = (kb0 + i) * GEMM_BK;
-        const int row_off = k_elem / p.a_k_wrap;
-        tma_load_2d(sa, &map_a, &full_bar[stage], k_elem - row_off * p.a_k_wrap, m_blk * GEMM_BM + row_off);
-        tma_load_2d(sa + Cfg::kStageBytesA, &map_b, &full_bar[stage], k_elem, n_blk * BN);
+      for (int g = n_pre; g < n_groups; ++g) {
+        const int slot = g % slots;
+        const uint32_t phase = (g / slots) & 1;
+        mbar_wait(&empty_bar[slot], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[slot], tx);
+        for (int j = 0; j < kps; ++j) {
+          uint8_t* sa = smem + (slot * kps + j) * Cfg::kStageBytes;
+          const int k_elem = (kb0 + g * kps + j) * GEMM_BK;
+          const int row_off = k_elem / p.a_k_wrap;
+          tma_load_2d(sa, &map_a, &full_bar[slot], k_elem - row_off * p.a_k_wrap, m_blk * GEMM_BM + row_off);
+          tma_load_2d(sa + Cfg::kStageBytesA, &map_b, &full_bar[slot], k_elem, n_blk * BN);
+        }
       }
     }
   } else if (warp == 5) {
     // -------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
-      for (int i = 0; i < nkb; ++i) {
-        const int stage = i % Cfg::kStages;
-        const uint32_t phase = (i / Cfg::kStages) & 1;
-        mbar_wait(&full_bar[stage], phase);
+      for (int g = 0; g < n_groups; ++g) {
+        const int slot = g % slots;
+        const uint32_t phase = (g / slots) & 1;
+        mbar_wait(&full_bar[slot], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint64_t adesc = umma_smem_desc_sw128(sa, 1024, 16);
-        const uint64_t bdesc = umma_smem_desc_sw128(sa + Cfg::kStageBytesA, 1024, 16);
+        for (int j = 0; j < kps; ++j) {
+          const uint32_t sa = smem_u32(smem + (slot * kps + j) * Cfg::kStageBytes);
+          const uint64_t adesc = umma_smem_desc_sw128(sa, 1024, 16);
+          const uint64_t bdesc = umma_smem_desc_sw128(sa + Cfg::kStageBytesA, 1024, 16);
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
-        umma_commit(&empty_bar[stage]);
+          for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (g | j | k) != 0);
+        }
+        umma_commit(&empty_bar[slot]);
       }
       umma_commit(acc_full);                                  // every MMA retired: accumulator complete, stage ring drained
     }
   } else if (warp < 4) {
-    // ------------------------------------------- spill this CTA's partial tile
     pdl_wait();
+    // Everything the epilogue needs from global memory is requested NOW, while the MMAs run: bias, RoPE angles, the
+    // fused norm's gamma / row statistics and the old residual values do not depend on the accumulator, and an L2 round
+    // trip after the reduction would sit on the dependency chain of the whole streaming step.
+    if (e_live) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+        for (int q = 0; q < kHalf / 4; ++q) {
+          const int n = n_blk * BN + hf * 32 + e_c0 + q * 4;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), gv = bv, xv = bv;
+          if (n < p.N) {
+            if (p.bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            if (p.xb_out != nullptr) gv = __ldg(reinterpret_cast<const float4*>(p.xb_gamma + n));
+            if (p.out_mode == OUT_F32_RESIDUAL) xv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + e_obase + n);
+          }
+          e_bias[hf][q * 4] = bv.x; e_bias[hf][q * 4 + 1] = bv.y; e_bias[hf][q * 4 + 2] = bv.z; e_bias[hf][q * 4 + 3] = bv.w;
+          e_gamma[hf][q * 4] = gv.x; e_gamma[hf][q * 4 + 1] = gv.y; e_gamma[hf][q * 4 + 2] = gv.z; e_gamma[hf][q * 4 + 3] = gv.w;
+          e_xold[hf][q * 4] = xv.x; e_xold[hf][q * 4 + 1] = xv.y; e_xold[hf][q * 4 + 2] = xv.z; e_xold[hf][q * 4 + 3] = xv.w;
+        }
+      if (p.rope_period > 0 && n_blk * BN < p.rope_cols) {
+        const int pos = p.rope_offset + e_r % p.rope_period;
+#pragma unroll
+        for (int j = 0; j < kHalf; ++j) {
+          e_cos[j] = __ldg(p.rope_cos + static_cast<long long>(e_c0 + j) * p.rope_ld + pos);
+          e_sin[j] = __ldg(p.rope_sin + static_cast<long long>(e_c0 + j) * p.rope_ld + pos);
+        }
+      }
+      if (p.row_stats != nullptr) e_rs = row_rs(p, e_g);
+    }
+    // ------------------------------------------- spill this CTA's partial tile
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const int row = warp * 32 + lane;                         // TMEM lane = tile row
@@ -167,90 +226,90 @@ gemm_splitk_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 
   if (warp < 4) {
     // ------------------------------- reduce 128/S rows over DSMEM + epilogue
-    constexpr int kRows = GEMM_BM / S;                        // rows of the tile this CTA finishes
-    constexpr int kHalf = 32 / S;                             // columns per thread in each half of a 64-wide block (4, 8, 16)
-    const int t = threadIdx.x;                                // 0..127
-    const int row = rank * kRows + t / S;
-    const int cseg = t % S;
-    const int g = m_blk * GEMM_BM + row;                      // A row
-    const int grp = g / p.grp_in;
-    const int r = g - grp * p.grp_in;
-    if (g < p.M && r < p.grp_valid) {
-      const long long obase = static_cast<long long>(grp) * p.grp_stride + p.grp_off + static_cast<long long>(r) * p.ldo;
-      const uint32_t prow = smem_u32(part) + row * (BN * 4);
-      const int sw = row & 7;
-      const bool do_rope = p.rope_period > 0;
-      const int pos = do_rope ? p.rope_offset + r % p.rope_period : 0;
+    float ss = 0.f;                                           // fused-RMSNorm producer: this thread's share of the row's sum of squares
+    if (e_live) {
+      const uint32_t prow = smem_u32(part) + e_row * (BN * 4);
+      const int sw = e_row & 7;
+      const int n0 = n_blk * BN;
+      float v[2][kHalf];
 #pragma unroll
-      for (int blk = 0; blk < BN / 64; ++blk) {
-        const int n0 = n_blk * BN + blk * 64;
-        if (n0 >= p.N) break;
-        float v[2][kHalf];
+      for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
+        for (int q = 0; q < kHalf / 4; ++q) {
+          const int chunk = (hf * 32 + e_c0 + q * 4) >> 2;
+          const uint32_t a = prow + ((chunk ^ sw) << 4);
+          float4 parts[S];
 #pragma unroll
-          for (int q = 0; q < kHalf / 4; ++q) {
-            const int chunk = (blk * 64 + hf * 32 + cseg * kHalf + q * 4) >> 2;
-            const uint32_t a = prow + ((chunk ^ sw) << 4);
-            float4 parts[S];
+          for (int s = 0; s < S; ++s) parts[s] = ld_dsmem_f4(mapa_shared(a, s));
+          float4 acc = parts[0];
 #pragma unroll
-            for (int s = 0; s < S; ++s) parts[s] = ld_dsmem_f4(mapa_shared(a, s));
-            float4 acc = parts[0];
-#pragma unroll
-            for (int s = 1; s < S; ++s) { acc.x += parts[s].x; acc.y += parts[s].y; acc.z += parts[s].z; acc.w += parts[s].w; }
-            v[hf][q * 4] = acc.x; v[hf][q * 4 + 1] = acc.y; v[hf][q * 4 + 2] = acc.z; v[hf][q * 4 + 3] = acc.w;
-          }
+          for (int s = 1; s < S; ++s) { acc.x += parts[s].x; acc.y += parts[s].y; acc.z += parts[s].z; acc.w += parts[s].w; }
+          v[hf][q * 4] = acc.x; v[hf][q * 4 + 1] = acc.y; v[hf][q * 4 + 2] = acc.z; v[hf][q * 4 + 3] = acc.w;
         }
-        const int c0 = cseg * kHalf;                          // first column (within a half) owned by this thread
-        if (p.bias != nullptr) {
+      }
+      if (p.row_stats != nullptr) {
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf)
+        for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
-            for (int j = 0; j < kHalf; ++j) {
-              const int n = n0 + hf * 32 + c0 + j;
-              if (n < p.N) v[hf][j] += __ldg(p.bias + n);
+          for (int j = 0; j < kHalf; ++j) v[hf][j] *= e_rs;
+      }
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+          for (int j = 0; j < kHalf; ++j) v[hf][j] += e_bias[hf][j];
+      }
+      if (p.act == ACT_GELU_TANH) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+          for (int j = 0; j < kHalf; ++j) v[hf][j] = gelu_tanh_f(v[hf][j]);
+      }
+      if (p.rope_period > 0 && n0 < p.rope_cols) {
+#pragma unroll
+        for (int j = 0; j < kHalf; ++j) {
+          const float x1 = v[0][j], x2 = v[1][j];
+          v[0][j] = x1 * e_cos[j] - x2 * e_sin[j];
+          v[1][j] = x1 * e_sin[j] + x2 * e_cos[j];
+        }
+      }
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+        for (int q = 0; q < kHalf / 4; ++q) {
+          const int n = n0 + hf * 32 + e_c0 + q * 4;
+          if (n >= p.N) continue;                             // N is a multiple of 8: whole float4 groups are in or out
+          const float* vv = &v[hf][q * 4];
+          if (p.out_mode == OUT_BF16) {
+            uint2 w;
+            w.x = pack_bf16x2(vv[0], vv[1]);
+            w.y = pack_bf16x2(vv[2], vv[3]);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + e_obase + n) = w;
+          } else {
+            float4 x = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            if (p.out_mode == OUT_F32_RESIDUAL) {
+              const float* old = &e_xold[hf][q * 4];
+              x.x += old[0]; x.y += old[1]; x.z += old[2]; x.w += old[3];
             }
-        }
-        if (p.act == ACT_GELU_TANH) {
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-            for (int j = 0; j < kHalf; ++j) v[hf][j] = gelu_tanh_f(v[hf][j]);
-        }
-        if (do_rope && n0 < p.rope_cols) {
-#pragma unroll
-          for (int j = 0; j < kHalf; ++j) {
-            const float cs = __ldg(p.rope_cos + static_cast<long long>(c0 + j) * p.rope_ld + pos);
-            const float sn = __ldg(p.rope_sin + static_cast<long long>(c0 + j) * p.rope_ld + pos);
-            const float x1 = v[0][j], x2 = v[1][j];
-            v[0][j] = x1 * cs - x2 * sn;
-            v[1][j] = x1 * sn + x2 * cs;
-          }
-        }
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-          for (int q = 0; q < kHalf / 4; ++q) {
-            const int n = n0 + hf * 32 + c0 + q * 4;
-            if (n >= p.N) continue;                           // N is a multiple of 8: whole float4 groups are in or out
-            const float* vv = &v[hf][q * 4];
-            if (p.out_mode == OUT_BF16) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + e_obase + n) = x;
+            if (p.xb_out != nullptr) {
+              const float* ga = &e_gamma[hf][q * 4];
+              ss = fmaf(x.x, x.x, ss); ss = fmaf(x.y, x.y, ss); ss = fmaf(x.z, x.z, ss); ss = fmaf(x.w, x.w, ss);
               uint2 w;
-              w.x = pack_bf16x2(vv[0], vv[1]);
-              w.y = pack_bf16x2(vv[2], vv[3]);
-              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + n) = w;
-            } else {
-              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + n);
-              float4 x = make_float4(vv[0], vv[1], vv[2], vv[3]);
-              if (p.out_mode == OUT_F32_RESIDUAL) {
-                const float4 old = *o;
-                x.x += old.x; x.y += old.y; x.z += old.z; x.w += old.w;
-              }
-              *o = x;
+              w.x = pack_bf16x2(x.x * ga[0], x.y * ga[1]);
+              w.y = pack_bf16x2(x.z * ga[2], x.w * ga[3]);
+              *reinterpret_cast<uint2*>(p.xb_out + e_orow * p.N + n) = w;
             }
           }
         }
       }
+    }
+    if (p.xb_out != nullptr) {
+      // the S threads of a row sit in consecutive lanes: fixed-order butterfly over them, lane cseg == 0 stores the chunk's sum
+      __syncwarp();
+#pragma unroll
+      for (int o = S / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (e_live && (threadIdx.x % S) == 0 && n_blk * BN < p.N) p.stat_out[e_orow * ((p.N + 63) / 64) + n_blk * (BN / 64)] = ss;
     }
   }
   __syncwarp();

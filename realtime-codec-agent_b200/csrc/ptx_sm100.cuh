@@ -40,7 +40,38 @@ __device__ __forceinline__ uint32_t elect_one() {
 // the PREVIOUS kernel has completed and its writes are visible.  Everything before pdl_wait() (barrier init, TMEM
 // allocation, descriptor prefetch) overlaps the predecessor's tail.  Both are no-ops for ordinary launches.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifndef MC_TRACE
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#else
+// Timeline build (python -m realtime_codec_agent_b200.build --trace; tools/trace_stream.py): thread 0 of every CTA logs
+// the global timer before and after its griddepcontrol.wait.  "after" of kernel i+1 minus "after" of kernel i is kernel
+// i's cost on the dependency chain of a graph replay; "before" shows whether launch + prologue were hidden by PDL.
+static __device__ unsigned long long* g_mc_trace = nullptr;
+static __device__ unsigned int g_mc_trace_cap = 0;
+static __device__ unsigned int g_mc_trace_n = 0;
+__device__ __forceinline__ unsigned long long mc_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void pdl_wait() {
+  if (threadIdx.x == 0 && g_mc_trace != nullptr) {
+    const unsigned long long t0 = mc_globaltimer();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const unsigned long long t1 = mc_globaltimer();
+    const unsigned int slot = atomicAdd(&g_mc_trace_n, 1u);
+    if (slot < g_mc_trace_cap) {
+      unsigned long long* r = g_mc_trace + 4ull * slot;
+      r[0] = (static_cast<unsigned long long>(gridDim.x * gridDim.y) << 32) | (blockIdx.x + blockIdx.y * gridDim.x);
+      r[1] = blockDim.x;
+      r[2] = t0;
+      r[3] = t1;
+    }
+  } else {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
+}
+#endif
 
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -191,7 +191,7 @@ vq_argmin_sm100_kernel(const __grid_constant__ CUtensorMap map_b, const float* _
   }
 }
 
-inline size_t vq_sm100_scratch_bytes(int num_sms, int Mq) { return (size_t)64 * Mq * sizeof(VqPartial); }
+inline size_t vq_sm100_scratch_bytes(int num_sms, int Mq) { return (size_t)148 * Mq * sizeof(VqPartial); }
 
 inline int launch_vq_sm100(mc_handle* h, const float* z, int n_items, int F, int keep, int64_t* codes, float* margin,
                            void* scratch, cudaStream_t stream) {
@@ -200,7 +200,8 @@ inline int launch_vq_sm100(mc_handle* h, const float* z, int n_items, int F, int
   const int tiles_total = s.codebook_size / VQ_BN;
   const int row_tiles = (Mq + 127) / 128;
   int splits = (h->num_sms + row_tiles - 1) / row_tiles;
-  splits = std::max(1, std::min(std::min(64, tiles_total), splits));
+  splits = std::max(1, std::min(std::min(148, tiles_total), splits));   // one row tile (a streaming frame): the whole chip scans the codebook
+  splits = (tiles_total + (tiles_total + splits - 1) / splits - 1) / ((tiles_total + splits - 1) / splits);   // no empty split
   const CUtensorMap* mb = nullptr;
   MC_TRY(mc_internal::get_map_2d_bf16(h, h->ptr<bf16>("vq.packed"), 64, (uint64_t)s.codebook_size, 64, VQ_BN, &mb));
   MC_TRY(mc_allow_smem(h, vq_argmin_sm100_kernel, VQ_SMEM_BYTES));

@@ -200,14 +200,14 @@ def test_session_reseed_after_one_shot_calls_is_an_upload(gen):
         (_, w1), _, _ = t.detokenize_audio(s_all)                          # 3.1 s of codes > 100 frames: stateless + re-seed
         (_, w2), _, _ = t.detokenize_audio(sink[3], preroll_samples=320)
         sink.append((w1, w2))
+    l0 = gen.launch_count
+    gen.encode(torch.from_numpy(wav[None, 1600:49600]).cuda(), keep_last_frames=150)   # the context keeps max(n_new, 2 s) samples
+    assert launches[0] == launches[1] == gen.launch_count - l0             # exactly one pass: the re-seed computes nothing
     # the same calls against windows built by hand (stateless calls with the session's kernels)
     gen.set_option("small_m_split_k", 2)
     ctx = wav[49600 + 5 * 1600 + 1600 - 32000: 49600 + 6 * 1600]
     want = gen.encode(torch.from_numpy(ctx[None]).cuda(), keep_last_frames=5)[0].cpu().numpy()
     assert [ord(c) - tok.unicode_offset for c in outs[7]] == list(want)
-    l0 = gen.launch_count
-    gen.encode(torch.from_numpy(wav[None, 1600:49600]).cuda(), keep_last_frames=150)   # the context keeps max(n_new, 2 s) samples
-    assert launches[0] == launches[1] == gen.launch_count - l0             # exactly one pass: the re-seed computes nothing
     assert outs[:8] == ref_outs[:8]                                        # graph replay == direct launches after the re-seed
     assert all(np.array_equal(a, b) for a, b in zip(outs[8], ref_outs[8]))
     # stateless reference for the decode that followed the re-seed of the code context

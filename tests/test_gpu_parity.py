@@ -383,6 +383,37 @@ def test_small_spec_parity_on_4800_frames(name):
     assert st["z_err_max"] <= Z_TOL and st["disagree_above_eps"] == 0 and st["agree_all"] >= AGREE_ALL_MIN
 
 
+def test_fused_norm_few_rows_path_agrees_with_the_unfused_one(bundle):
+    """Few-rows path (sessions / small_m_split_k = 2): RMSNorms folded into the GEMM epilogues around them (producer emits
+    bf16(x * gamma) + per-row sums of squares, consumer scales accumulator rows) against the same path with standalone
+    rmsnorm kernels: same mathematics, other rounding points — latents within the engine-vs-oracle noise, decoded audio
+    within 40 dB (the engine itself sits 43 dB from the fp32 oracle), codes equal outside near-ties."""
+    name, spec, w, g, gen = bundle
+    x = torch.from_numpy(np.stack([g["wav0"][-32000:], g["wav1"][-32000:]])).cuda()
+    outs = {}
+    try:
+        gen.set_option("small_m_split_k", 2)
+        for fuse in (1, 0):
+            gen.set_option("fuse_norm", fuse)
+            l0 = gen.launch_count
+            c, m, z = gen.encode(x[:1], return_margin=True, return_latents=True)
+            launches = gen.launch_count - l0
+            rec = gen.decode(torch.from_numpy(g["tap_idx"]).long().cuda()[:1])
+            outs[fuse] = (c, m, z, rec, launches)
+    finally:
+        gen.set_option("fuse_norm", 1)
+        gen.set_option("small_m_split_k", 1)
+    (c1, m1, z1, r1, l1), (c0, m0, z0, r0, l0_) = outs[1], outs[0]
+    assert l1 == l0_ - (2 * spec.enc_layers + 1)                       # every encoder norm left the launch list
+    dz = (z1 - z0).abs().max().item()
+    clear = torch.minimum(m1, m0) > 0.1
+    _report(name, fused_vs_unfused_dz=round(dz, 4), codes_equal=round((c1 == c0).float().mean().item(), 3), decode_snr_db=round(_snr_db(r0, r1), 1))
+    assert dz < 0.03 and torch.equal(c1[clear], c0[clear]) and _snr_db(r0, r1) > 40.0
+    # and against the oracle's golden latents, like the unfused path
+    z_ref = torch.from_numpy(g["tap_z_e"]).cuda()[:1]
+    assert (z1 - z_ref).abs().max().item() <= Z_TOL
+
+
 @pytest.mark.parametrize("mode", [0, 2])
 def test_stream_session_equals_stateless_calls(bundle, mode):
     """mc_stream_* (device-resident context + CUDA-graph replay) == re-sending the whole window, with the batch-invariant
