@@ -205,9 +205,7 @@ int launch_gemm(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   if (c.xb_out && (c.out_mode == OUT_BF16 || c.N % 64 != 0 || !c.xb_gamma || !c.stat_out))
     return h->fail(MC_ERR_ARG, "gemm: fused RMSNorm producer needs an fp32 output, N %% 64 == 0, gamma and a stats buffer");
   if (bn >= 1002 && bn <= 1008) return launch_gemm_splitk(h, c, bn - 1000, stream);   // forced (tests / A-B timing)
-  if (bn == 2064) return launch_gemm_bn<64, 64>(h, c, stream);                        // 64-row UMMA tiles
-  if (bn == 3064 && (c.K / GEMM_BK) % 2 == 0) return launch_gemm_bn<64, GEMM_BM, 2>(h, c, stream);   // 2 k-blocks per barrier round trip
-  if (bn == 4064 && (c.K / GEMM_BK) % 4 == 0) return launch_gemm_bn<64, GEMM_BM, 4>(h, c, stream);   // 4
+  if (bn == 4064 && (c.K / GEMM_BK) % 4 == 0) return launch_gemm_bn<64, GEMM_BM, 4>(h, c, stream);   // forced: 4 k-blocks per barrier round trip
   if (bn == 0 && (h->split_k == 2 || (h->split_k == 1 && h->in_session))) {
     const int S = pick_split_k(h, c);
     if (S >= 2) return launch_gemm_splitk(h, c, S, stream);

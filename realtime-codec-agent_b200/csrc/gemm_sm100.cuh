@@ -510,15 +510,19 @@ __device__ __forceinline__ void gemm_epilogue_slab_fast(const GemmParams& p, con
   }
 }
 
-// BM = 64: 64-row UMMA tiles for few-rows GEMMs.  A tcgen05.mma streams its A rows at one row per clock (measured: 128
-// cycles per M = 128 dispatch whatever N, in 128-byte- or 32-byte-swizzled layout; profiles/r02_small_gemm_chain.log), so
-// a 100-row GEMM as 2 x 64 rows on twice the CTAs halves the K loop; the K order per output element is unchanged.  The
-// 64 accumulator rows sit in TMEM lanes 32q .. 32q+15 (q = 0..3): warp q drains rows 16q .. 16q+15 with lanes 0..15.
+// BM: rows per UMMA tile (only 128 is instantiated; 64 — accumulator rows in TMEM lanes 32q .. 32q+15, drained by lanes
+// 0..15 of epilogue warp q — computes bit-identical results but was not faster, see below).
 //
 // KPS = 64-wide k-blocks per pipeline stage (per full/empty barrier round trip).  With small tiles the loop is not bound
 // by the tensor pipe or by operand traffic but by the issuing thread's own round trip (mbarrier try_wait, fence, four
 // tcgen05.mma, tcgen05.commit: ~550 cycles per k-block whatever M, N or the smem layout — tools/diag_small_gemm.py);
 // KPS > 1 puts several k-blocks behind ONE wait and ONE commit.
+// What does NOT move the remaining ~90 cycles per tcgen05.mma at these tile sizes (all built, measured in a dependent
+// chain and removed again; profiles/r02_small_gemm_chain_experiments.log): 64-row UMMA tiles on twice the CTAs (BM = 64:
+// 7.9 -> 7.8 us, with KPS = 4 6.5 -> 6.3 us), the A operand in 32-byte-swizzled K = 16 slices (slower: four TMA
+// boxes per k-block), two issuing threads on alternate k-groups with two accumulators (6.51 -> 6.49 us), N = 16
+// instead of 64.  It is a per-instruction cost of the tensor pipe for shared-memory operands, so the only lever left
+// is FEWER instructions per CTA: K split over a cluster (gemm_splitk_sm100.cuh) where the tile count allows.
 template <int BN, int BM = GEMM_BM, int KPS = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
