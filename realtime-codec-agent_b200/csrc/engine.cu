@@ -1058,6 +1058,7 @@ struct mc_stream {
   float* audio[2] = {nullptr, nullptr};
   int64_t* codes_ctx[2] = {nullptr, nullptr};
   int audio_len = 0, code_len = 0, acur = 0, ccur = 0;
+  int32_t* pin_table = nullptr; // {0, current context buffer}: read in place by the roll kernel
   float* pin_audio = nullptr;   // [C, cap_samples]
   int64_t* pin_codes = nullptr; // [C, cap_frames]
   float* pin_wav = nullptr;     // [C, cap_samples]
@@ -1173,6 +1174,7 @@ int mc_stream_create(mc_handle* h, int32_t channels, int32_t context_samples, in
   }
   if (e == cudaSuccess) e = cudaMalloc(&s->dev_codes_out, cb);
   if (e == cudaSuccess) e = cudaMalloc(&s->dev_wav_out, ab);
+  if (e == cudaSuccess) e = cudaMallocHost(&s->pin_table, 16);
   if (e == cudaSuccess) e = cudaMallocHost(&s->pin_audio, ab);
   if (e == cudaSuccess) e = cudaMallocHost(&s->pin_codes, cb);
   if (e == cudaSuccess) e = cudaMallocHost(&s->pin_wav, ab);
@@ -1189,6 +1191,7 @@ int mc_stream_destroy(mc_stream* s) {
   for (int i = 0; i < 2; ++i) { if (s->audio[i]) cudaFree(s->audio[i]); if (s->codes_ctx[i]) cudaFree(s->codes_ctx[i]); }
   if (s->dev_codes_out) cudaFree(s->dev_codes_out);
   if (s->dev_wav_out) cudaFree(s->dev_wav_out);
+  if (s->pin_table) cudaFreeHost(s->pin_table);
   if (s->pin_audio) cudaFreeHost(s->pin_audio);
   if (s->pin_codes) cudaFreeHost(s->pin_codes);
   if (s->pin_wav) cudaFreeHost(s->pin_wav);
@@ -1272,14 +1275,14 @@ int mc_stream_push_audio(mc_stream* s, const float* chunk, int32_t n, int32_t ke
   for (int c = 0; c < C; ++c) memcpy(s->pin_audio + (size_t)c * cap, chunk + (size_t)c * n, (size_t)n * 4);
   const int src = s->acur, dst = s->acur ^ 1;
   const int old_len = s->audio_len;
+  // One kernel rolls the context (kept tail ++ the new chunk, read in place from pinned host memory) and the last
+  // kernel of the pass writes the codes straight into pinned host memory: no copy nodes on the latency path.
+  s->pin_table[0] = 0; s->pin_table[1] = src;
   auto body = [&]() -> int {
-    if (keep_old > 0)
-      MC_CUDA(h, cudaMemcpy2DAsync(s->audio[dst], (size_t)cap * 4, s->audio[src] + (old_len - keep_old), (size_t)cap * 4,
-                                   (size_t)keep_old * 4, C, cudaMemcpyDeviceToDevice, stream));
-    MC_CUDA(h, cudaMemcpy2DAsync(s->audio[dst] + keep_old, (size_t)cap * 4, s->pin_audio, (size_t)cap * 4, (size_t)n * 4, C,
-                                 cudaMemcpyHostToDevice, stream));
-    MC_TRY(encode_impl(h, s->audio[dst], cap, C, new_len, keep, s->dev_codes_out, nullptr, nullptr, stream));
-    MC_CUDA(h, cudaMemcpyAsync(s->pin_codes, s->dev_codes_out, (size_t)C * keep * 8, cudaMemcpyDeviceToHost, stream));
+    pool_roll_kernel<float><<<dim3((new_len + 255) / 256, C), 256, 0, stream>>>(s->pin_table, C, cap, old_len, keep_old, n, s->audio[0],
+                                                                               s->audio[1], s->pin_audio, nullptr, 0);
+    MC_LAUNCH_CHECK(h, "pool_roll_kernel");
+    MC_TRY(encode_impl(h, s->audio[dst], cap, C, new_len, keep, s->pin_codes, nullptr, nullptr, stream));
     return MC_OK;
   };
   MC_TRY(run_or_replay(s, std::make_tuple(0, old_len, n, keep, src), stream, body));
@@ -1332,23 +1335,21 @@ static int stream_push_codes_impl(mc_stream* s, const int64_t* codes, int32_t n,
   const int old_len = s->code_len;
   const int emit_floats = 2 * s->emit_chunk + s->emit_fade;
   // decode_impl wants dense [C, new_len] codes: the context buffers use row stride `cap`, so gather rows densely
+  s->pin_table[0] = 0; s->pin_table[1] = src;
   auto body = [&]() -> int {
-    if (keep_old > 0)
-      MC_CUDA(h, cudaMemcpy2DAsync(s->codes_ctx[dst], (size_t)cap * 8, s->codes_ctx[src] + (old_len - keep_old), (size_t)cap * 8,
-                                   (size_t)keep_old * 8, C, cudaMemcpyDeviceToDevice, stream));
-    MC_CUDA(h, cudaMemcpy2DAsync(s->codes_ctx[dst] + keep_old, (size_t)cap * 8, s->pin_codes, (size_t)cap * 8, (size_t)n * 8, C,
-                                 cudaMemcpyHostToDevice, stream));
-    MC_CUDA(h, cudaMemcpy2DAsync(s->dev_codes_out, (size_t)new_len * 8, s->codes_ctx[dst], (size_t)cap * 8, (size_t)new_len * 8, C,
-                                 cudaMemcpyDeviceToDevice, stream));
-    MC_TRY(decode_impl(h, s->dev_codes_out, nullptr, C, new_len, keep, s->dev_wav_out, stream));
+    // one kernel: context roll (codes read in place from pinned host memory) + the dense [C, new_len] batch the decoder reads
+    pool_roll_kernel<long long><<<dim3((new_len + 255) / 256, C), 256, 0, stream>>>(
+        s->pin_table, C, cap, old_len, keep_old, n, reinterpret_cast<long long*>(s->codes_ctx[0]), reinterpret_cast<long long*>(s->codes_ctx[1]),
+        reinterpret_cast<const long long*>(s->pin_codes), reinterpret_cast<long long*>(s->dev_codes_out), new_len);
+    MC_LAUNCH_CHECK(h, "pool_roll_kernel");
     if (emit) {
+      MC_TRY(decode_impl(h, s->dev_codes_out, nullptr, C, new_len, keep, s->dev_wav_out, stream));
       mc_launch(h, emit_chunk_kernel, dim3(1), dim3(POST_THREADS), 0, stream, (const float*)s->dev_wav_out, keep, s->emit_chunk,
                 s->emit_fade, has_prev, s->emit_target_rms, s->emit_silence_thr, (const float*)s->emit_fade_in, s->emit_prev_tail,
-                s->emit_out);
+                s->pin_emit);                                  // the emitted block lands in pinned host memory directly
       MC_LAUNCH_CHECK(h, "emit_chunk_kernel");
-      MC_CUDA(h, cudaMemcpyAsync(s->pin_emit, s->emit_out, (size_t)emit_floats * 4, cudaMemcpyDeviceToHost, stream));
     } else {
-      MC_CUDA(h, cudaMemcpyAsync(s->pin_wav, s->dev_wav_out, (size_t)C * keep * 4, cudaMemcpyDeviceToHost, stream));
+      MC_TRY(decode_impl(h, s->dev_codes_out, nullptr, C, new_len, keep, s->pin_wav, stream));   // last kernel stores to pinned host memory
     }
     return MC_OK;
   };

@@ -147,6 +147,7 @@ embed_distance_kernel(const long long* __restrict__ ids, int n, long long vocab_
 // the n sessions of a batch (kept tail of the old context ++ the staged new chunk, audio_tokenizer.py:72-74 /
 // :111-113) and gathers them into the dense [n*C, ld] batch the encoder / decoder reads.
 //   table[2j] = slot of batch item j, table[2j+1] = which of the two context buffers currently holds it
+// `table` and `staged` may be PINNED HOST memory read in place (single sessions: one kernel instead of three copy nodes).
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -158,12 +159,12 @@ pool_roll_kernel(const int* __restrict__ table, int C, int cap, int old_len, int
   const T* src = (par ? ctx1 : ctx0) + (static_cast<long long>(slot) * C + c) * cap;
   T* dst = (par ? ctx0 : ctx1) + (static_cast<long long>(slot) * C + c) * cap;
   const T* st = staged + static_cast<long long>(jc) * cap;
-  T* bt = batch + static_cast<long long>(jc) * batch_ld;
+  T* bt = batch != nullptr ? batch + static_cast<long long>(jc) * batch_ld : nullptr;   // NULL: the consumer reads the context itself
   const int new_len = keep_old + n_new;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < new_len; i += gridDim.x * blockDim.x) {
     const T v = i < keep_old ? src[old_len - keep_old + i] : st[i - keep_old];
     dst[i] = v;
-    bt[i] = v;
+    if (bt != nullptr) bt[i] = v;
   }
 }
 
