@@ -4,8 +4,9 @@ import csv
 import re
 import sys
 
-CLASSES = [("gemm", r"gemm2?_bf16_sm100"), ("attention", r"attention_window"), ("vq", r"vq_"),
-           ("elementwise", r"rmsnorm|conv_first|gather_stem|compact_rows|embed_codes|tconv_last|emit_chunk|pack_latents")]
+CLASSES = [("gemm", r"gemm2?_bf16_sm100|gemm_splitk_sm100"), ("attention", r"attention_window"), ("vq", r"vq_"),
+           ("elementwise", r"rmsnorm|conv_first|gather_stem|compact_rows|embed_codes|tconv_last|emit_chunk|pack_latents|zero_pads|"
+                           r"pool_roll|pcm_to_f32|resample_poly")]
 rows = list(csv.DictReader(l for l in open(sys.argv[1]) if l.startswith('"')))
 tot, other = {c: [0.0, 0] for c, _ in CLASSES}, [0.0, 0]
 for r in rows:
