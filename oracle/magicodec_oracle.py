@@ -1,4 +1,8 @@
-"""ORACLE — test infrastructure only.  PARITY UNPINNED BY THE REFERENCE.
+"""ORACLE — test infrastructure only.  ARCHITECTURE UNPINNED BY THE REFERENCE; attention / rotary / RMSNorm semantics
+PINNED to the reference's named kernel dependency, flash-attention 2.8.3 (tests/test_gpu_flash_attn_pin.py, run on B200:
+this module's SDPA + band mask == flash_attn_func(causal=True, window_size=(32, 0)) up to flash-attn's bf16 output
+rounding, apply_rope == flash_attn.layers.rotary.apply_rotary_emb(interleaved=False) to 5e-7, _RMSNorm ==
+flash_attn.ops.triton.layer_norm.rms_norm_fn to 1e-6; magicodec_build.sh:4-16 builds exactly those kernels).
 
 fp32 PyTorch restatement of the MagiCodec network behind
 /root/reference/realtime_codec_agent/audio_tokenizer.py.  Only ``tests/``,
