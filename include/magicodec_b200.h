@@ -103,6 +103,16 @@ int mc_vq_search(mc_handle* h, const float* z, int32_t M, int64_t* codes, float*
 /* Copies the cached projected codebook, fp32 [K, dq]. */
 int mc_codebook(mc_handle* h, float* out, mc_stream_t stream);
 
+/* GEMM with an RMSNorm folded into it: consumer — y = acc * rsqrt(sum(row_stats[row][0..n)) / K + eps) + bias
+ * with A = bf16(x * gamma); producer (fp32 output modes) — additionally xb_out = bf16(x_new * xb_gamma) [M, N] and
+ * stat_out [M, N/64] = per-row sums of x_new^2 per 64 columns.  mc_op_rowstats: the same pair from an fp32 matrix.
+ * Stand in for csrc/layer_norm (dropout_add_rms_norm) + the linear that follows it (magicodec_build.sh:10-16). */
+int mc_op_gemm_fused(mc_handle* h, const void* A, const void* W, const float* bias, int32_t M, int32_t N, int32_t K, int32_t act,
+                     int32_t out_mode, void* out, const float* row_stats, int32_t row_stats_n, void* xb_out, const float* xb_gamma,
+                     float* stat_out, int32_t rope_cols, int32_t rope_period, int32_t block_n, mc_stream_t stream);
+int mc_op_rowstats(mc_handle* h, const float* x, const float* gamma, void* xb_out, float* stat_out, int32_t M, int32_t d,
+                   mc_stream_t stream);
+
 /* Debug: timeline of a pass (only in a library built with -DMC_TRACE; MC_ERR_STATE otherwise). */
 int64_t mc_debug_trace(mc_handle* h, void* dev_buf, int64_t capacity_records);
 

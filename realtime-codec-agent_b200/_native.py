@@ -78,6 +78,8 @@ SYMBOLS = {
     "mc_op_resample": (C.c_int, [_P, _P, _I64, _I32, _I64, _I32, _I32, _P, _I32, _I64, _P, _I64, _I64, _P]),
     "mc_flac_info": (C.c_int, [_P, _I64, C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I64)]),
     "mc_flac_decode": (C.c_int, [_P, _I64, _P, _I64, C.POINTER(_I64)]),
+    "mc_op_gemm_fused": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _I32, _P, _P, _P, _I32, _I32, _I32, _P]),
+    "mc_op_rowstats": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P]),
     "mc_op_rmsnorm": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P]),
     "mc_op_attention": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P]),
 }

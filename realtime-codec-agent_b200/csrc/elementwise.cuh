@@ -312,4 +312,47 @@ zero_pads_kernel(const PadList pl, int items) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// First producer of a stack whose RMSNorms live in GEMM epilogues (GemmParams: fused RMSNorm): x fp32 [M, d] ->
+// xb = bf16(x * gamma) [M, d] and stats[M, d/64] = per-row, per-64-column sums of x^2, with exactly the arithmetic of
+// the GEMM producers (sequential fmaf chain over the chunk, __fmul_rn before the bf16 rounding), so that a stack entered
+// through this kernel and one entered through a producing GEMM agree bit for bit.  One thread = one 64-column chunk.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rowstats_cast_kernel(const float* __restrict__ x, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ xb,
+                     float* __restrict__ stats, long long M, int d) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int nst = d >> 6;
+  const long long total = M * nst;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / nst;
+    const int c = static_cast<int>(i - row * nst);
+    const float4* src = reinterpret_cast<const float4*>(x + row * d + c * 64);
+    const float4* gsrc = reinterpret_cast<const float4*>(gamma + c * 64);
+    float v[64];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 a = src[j];
+      v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = a.z; v[4 * j + 3] = a.w;
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) ss = fmaf(v[j], v[j], ss);
+    uint4* dst = reinterpret_cast<uint4*>(xb + row * d + c * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 g0 = __ldg(gsrc + 2 * j), g1 = __ldg(gsrc + 2 * j + 1);
+      uint4 w;
+      w.x = pack_bf16x2(__fmul_rn(v[8 * j], g0.x), __fmul_rn(v[8 * j + 1], g0.y));
+      w.y = pack_bf16x2(__fmul_rn(v[8 * j + 2], g0.z), __fmul_rn(v[8 * j + 3], g0.w));
+      w.z = pack_bf16x2(__fmul_rn(v[8 * j + 4], g1.x), __fmul_rn(v[8 * j + 5], g1.y));
+      w.w = pack_bf16x2(__fmul_rn(v[8 * j + 6], g1.z), __fmul_rn(v[8 * j + 7], g1.w));
+      dst[j] = w;
+    }
+    stats[i] = ss;
+  }
+}
+
 }  // namespace mc

@@ -75,10 +75,11 @@ int launch_gemm_bn(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
 // CTA-pair kernel: 256 x 256 tiles on 74 clusters of two CTAs
 template <int EPI>
 int launch_gemm_pair_epi(mc_handle* h, const GemmParams& p, const CUtensorMap* ma, const CUtensorMap* mb,
-                         const CUtensorMap* mo, int pairs, cudaStream_t stream) {
+                         const CUtensorMap* mo, const CUtensorMap* mo2, int pairs, cudaStream_t stream) {
   constexpr int BN = 256;
-  MC_TRY(mc_allow_smem(h, gemm2_bf16_sm100_kernel<BN, EPI>, Gemm2Cfg<BN>::kSmemBytes));
-  mc_launch(h, gemm2_bf16_sm100_kernel<BN, EPI>, dim3(2 * pairs), dim3(GEMM_THREADS), Gemm2Cfg<BN>::kSmemBytes, stream, *ma, *mb, *mo, p);
+  MC_TRY(mc_allow_smem(h, gemm2_bf16_sm100_kernel<BN, EPI>, Gemm2Cfg<BN, EPI>::kSmemBytes));
+  mc_launch(h, gemm2_bf16_sm100_kernel<BN, EPI>, dim3(2 * pairs), dim3(GEMM_THREADS), Gemm2Cfg<BN, EPI>::kSmemBytes, stream, *ma, *mb,
+            *mo, *mo2, p);
   MC_LAUNCH_CHECK(h, "gemm2_bf16_sm100_kernel");
   return MC_OK;
 }
@@ -88,12 +89,17 @@ int launch_gemm_pair(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   const CUtensorMap *ma, *mb;
   MC_TRY(get_map_2d_bf16(h, c.A, (uint64_t)c.a_k_wrap, (uint64_t)c.a_rows, GEMM_BK, GEMM_BM, &ma));
   MC_TRY(get_map_2d_bf16(h, c.W, (uint64_t)c.K, (uint64_t)c.N, GEMM_BK, BN / 2, &mb));
-  const bool tma_out = (c.grp_in == INT_MAX);
+  // fused-RMSNorm producer: the specialised epilogue (x_old in through TMA) when its conditions hold, else per-thread stores
+  const bool norm_fast = c.xb_out != nullptr && h->fast_epilogue && c.grp_in == INT_MAX && c.bias != nullptr && c.N % BN == 0 &&
+                         c.out_mode == OUT_F32_RESIDUAL && c.act == ACT_NONE && c.rope_period == 0 && c.ldo == c.N;
+  const bool tma_out = (c.grp_in == INT_MAX) && (c.xb_out == nullptr || norm_fast);
   const CUtensorMap* mo = ma;
+  const CUtensorMap* mo2 = ma;
   if (tma_out) {
     const int esize = c.out_mode == OUT_BF16 ? 2 : 4;
     MC_TRY(get_map_2d(h, c.out, esize, (uint64_t)c.N, (uint64_t)c.M, (uint64_t)c.ldo * esize, esize == 2 ? 64 : 32, 32, &mo));
   }
+  if (norm_fast) MC_TRY(get_map_2d(h, c.xb_out, 2, (uint64_t)c.N, (uint64_t)c.M, (uint64_t)c.N * 2, 64, 32, &mo2));
   GemmParams p;
   p.tma_store = tma_out ? 1 : 0;
   p.M = c.M; p.N = c.N; p.K = c.K; p.a_k_wrap = c.a_k_wrap;
@@ -103,6 +109,7 @@ int launch_gemm_pair(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   p.rope_ld = h->spec.max_positions;
   p.rope_cos = c.rope_period > 0 ? h->ptr<float>("rope.cos") : nullptr;
   p.rope_sin = c.rope_period > 0 ? h->ptr<float>("rope.sin") : nullptr;
+  fill_norm_fields(h, c, p);
   const int m_tiles = (c.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM), n_tiles = (c.N + BN - 1) / BN;
   const int pairs = std::min(m_tiles * n_tiles, h->num_sms / 2);
   const double valid_rows = c.grp_in == INT_MAX ? (double)c.M : (double)c.M / c.grp_in * c.grp_valid;
@@ -110,13 +117,14 @@ int launch_gemm_pair(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   McProfScope prof(h, 0, 2.0 * valid_rows * c.N * c.K, valid_rows * c.a_k_wrap * 2.0 + (double)c.N * c.K * 2.0 + out_bytes, stream);
   // specialised epilogues (gemm_sm100.cuh): TMA-store output, bias, whole 256-column tiles, rope on 64-wide heads
   const bool fast_ok = h->fast_epilogue && tma_out && c.bias != nullptr && c.N % BN == 0;
+  if (norm_fast) return launch_gemm_pair_epi<EPI_RESID_NORM>(h, p, ma, mb, mo, mo2, pairs, stream);
   if (fast_ok && c.out_mode == OUT_BF16 && c.act == ACT_NONE && c.rope_period > 0 && c.rope_cols % 64 == 0)
-    return launch_gemm_pair_epi<EPI_ROPE_BF16>(h, p, ma, mb, mo, pairs, stream);
+    return launch_gemm_pair_epi<EPI_ROPE_BF16>(h, p, ma, mb, mo, mo2, pairs, stream);
   if (fast_ok && c.out_mode == OUT_BF16 && c.act == ACT_GELU_TANH && c.rope_period == 0)
-    return launch_gemm_pair_epi<EPI_GELU_BF16>(h, p, ma, mb, mo, pairs, stream);
-  if (fast_ok && c.out_mode == OUT_F32_RESIDUAL && c.act == ACT_NONE && c.rope_period == 0)
-    return launch_gemm_pair_epi<EPI_RESID_F32>(h, p, ma, mb, mo, pairs, stream);
-  return launch_gemm_pair_epi<EPI_GENERIC>(h, p, ma, mb, mo, pairs, stream);
+    return launch_gemm_pair_epi<EPI_GELU_BF16>(h, p, ma, mb, mo, mo2, pairs, stream);
+  if (fast_ok && c.out_mode == OUT_F32_RESIDUAL && c.act == ACT_NONE && c.rope_period == 0 && c.xb_out == nullptr)
+    return launch_gemm_pair_epi<EPI_RESID_F32>(h, p, ma, mb, mo, mo2, pairs, stream);
+  return launch_gemm_pair_epi<EPI_GENERIC>(h, p, ma, mb, mo, mo2, pairs, stream);
 }
 
 // Few-rows GEMM with K split over a cluster (gemm_splitk_sm100.cuh): S CTAs per 128 x 64 output tile.
@@ -201,7 +209,6 @@ int launch_gemm(mc_handle* h, const GemmCall& c, cudaStream_t stream) {
   if (c.rope_period > 0 && c.rope_period + c.rope_offset > h->spec.max_positions)
     return h->fail(MC_ERR_ARG, "gemm: rope period %d exceeds table rows %d", c.rope_period, h->spec.max_positions);
   int bn = c.block_n;
-  if ((c.row_stats || c.xb_out) && c.M > 2 * GEMM_BM) return h->fail(MC_ERR_ARG, "gemm: fused RMSNorm is a few-rows (M <= 256) feature");
   if (c.xb_out && (c.out_mode == OUT_BF16 || c.N % 64 != 0 || !c.xb_gamma || !c.stat_out))
     return h->fail(MC_ERR_ARG, "gemm: fused RMSNorm producer needs an fp32 output, N %% 64 == 0, gamma and a stats buffer");
   if (bn >= 1002 && bn <= 1008) return launch_gemm_splitk(h, c, bn - 1000, stream);   // forced (tests / A-B timing)
@@ -293,8 +300,22 @@ struct StackBufs {
 
 // RMSNorm folded into the neighbouring GEMMs (GemmParams: producer / consumer): only on the few-rows path, i.e. under the
 // same switch as the split-K kernels, so that a session and a stateless call in the same mode run identical kernels.
+bool few_rows_regime(const mc_handle* h, long long M) {
+  return (h->split_k == 2 || (h->split_k == 1 && h->in_session)) && M <= 2 * GEMM_BM;
+}
+// fuse_norm: 0 never; 1 few-rows path only (default); 2 every size, Wo and W2 produce; 3 every size, only Wo produces
+// (norm1 stays a kernel) — 2 / 3 are the offline variants measured in DESIGN.md §8.
 bool fuse_norm_ok(const mc_handle* h, long long M) {
-  return h->fuse_norm && (h->split_k == 2 || (h->split_k == 1 && h->in_session)) && M <= 2 * GEMM_BM && h->spec.d_model % 64 == 0;
+  if (h->spec.d_model % 64 != 0 || h->fuse_norm == 0) return false;
+  return h->fuse_norm >= 2 || few_rows_regime(h, M);
+}
+
+// x [M, d] -> b.hbuf = bf16(x * gamma), b.stats: the first producer of a fused stack when no GEMM can play that role
+int launch_rowstats(mc_handle* h, const float* x, const float* gamma, bf16* xb, float* stats, long long M, int d, cudaStream_t stream) {
+  McProfScope prof(h, 3, 0.0, (double)M * d * 6.0, stream);
+  mc_launch(h, rowstats_cast_kernel, dim3(ew_grid(h, M * (d / 64), 256)), dim3(256), 0, stream, x, gamma, xb, stats, M, d);
+  MC_LAUNCH_CHECK(h, "rowstats_cast_kernel");
+  return MC_OK;
 }
 
 // Runs n_layers blocks over B windows of F frames held in b.x and returns, in *x_out, the residual
@@ -311,11 +332,13 @@ bool fuse_norm_ok(const mc_handle* h, long long M) {
 // launched.  final_gamma (may be NULL) is the weight of the norm that FOLLOWS the stack: the last W2 emits that
 // operand, returned with its statistics through xb_out / stats_out.
 int run_layers(mc_handle* h, const char* prefix, int n_layers, const StackBufs& b, int B, int F, int keep_rows,
-               float** x_out, cudaStream_t stream, bool fused = false, const float* final_gamma = nullptr,
-               bf16** xb_out = nullptr, float** stats_out = nullptr) {
+               float** x_out, cudaStream_t stream, int fuse_mode = 0 /* 0 none, 1 every norm, 2 only norm2 (Wo -> W1) */,
+               const float* final_gamma = nullptr, bf16** xb_out = nullptr, float** stats_out = nullptr) {
   const mc_spec& s = h->spec;
   const int d = s.d_model, f = s.ffn_dim;
   const int nst = d / 64;
+  const bool fused = fuse_mode == 1;        // norm1 in (W2 | first producer) -> QKV
+  const bool fused2 = fuse_mode != 0;       // norm2 in Wo -> W1
   std::vector<int> r_in(n_layers), r_out(n_layers);
   {
     int need = std::max(1, std::min(keep_rows, F));
@@ -366,11 +389,11 @@ int run_layers(mc_handle* h, const char* prefix, int n_layers, const StackBufs& 
     o.A = b.att; o.a_rows = Mo; o.a_k_wrap = d; o.W = h->ptr<bf16>(T("wo")); o.bias = h->ptr<float>(T("bo"));
     o.M = Mo; o.N = d; o.K = d; o.act = ACT_NONE; o.out_mode = OUT_F32_RESIDUAL; o.out = x; o.ldo = d;
     o.prefetch_ptr = h->ptr<bf16>(T("w1")); o.prefetch_bytes = (long long)f * d * 2;
-    if (fused) { o.xb_out = b.hbuf; o.xb_gamma = h->ptr<float>(T("norm2")); o.stat_out = b.stats; }
+    if (fused2) { o.xb_out = b.hbuf; o.xb_gamma = h->ptr<float>(T("norm2")); o.stat_out = b.stats; }
     MC_TRY(launch_gemm(h, o, stream));
-    if (!fused) MC_TRY(launch_rmsnorm(h, x, h->ptr<float>(T("norm2")), b.hbuf, Mo, d, INT_MAX, 0, 0, stream));
+    if (!fused2) MC_TRY(launch_rmsnorm(h, x, h->ptr<float>(T("norm2")), b.hbuf, Mo, d, INT_MAX, 0, 0, stream));
     GemmCall u{};
-    if (fused) { u.row_stats = b.stats; u.row_stats_n = nst; }
+    if (fused2) { u.row_stats = b.stats; u.row_stats_n = nst; }
     u.A = b.hbuf; u.a_rows = Mo; u.a_k_wrap = d; u.W = h->ptr<bf16>(T("w1")); u.bias = h->ptr<float>(T("b1"));
     u.M = Mo; u.N = f; u.K = d; u.act = ACT_GELU_TANH; u.out_mode = OUT_BF16; u.out = b.ffn; u.ldo = f;
     u.prefetch_ptr = h->ptr<bf16>(T("w2")); u.prefetch_bytes = (long long)d * f * 2;
@@ -406,7 +429,7 @@ int run_layers(mc_handle* h, const char* prefix, int n_layers, const StackBufs& 
     MC_LAUNCH_CHECK(h, "compact_rows_kernel");
     std::swap(x, xalt);
   }
-  if (fused && rows > keep_rows && B != 1) return h->fail(MC_ERR_STATE, "run_layers: fused norms with a trailing compaction");
+  if (fused && final_gamma && rows > keep_rows && B != 1) return h->fail(MC_ERR_STATE, "run_layers: fused norms with a trailing compaction");
   *x_out = x;
   if (xb_out) *xb_out = xb;
   if (stats_out) *stats_out = st;
@@ -563,7 +586,11 @@ int encode_impl(mc_handle* h, const float* wav, int64_t ld, int B, int T, int ke
   const bool shared = h->shared_stem && B >= 2 && ld > 0 && ld < T && ld % hop == 0 && T % hop == 0 && F > pre &&
                       span_samples <= INT_MAX && span_frames + (long long)pre * B < (long long)B * F / 2;
   // RMSNorms inside GEMM epilogues on the few-rows path (the keep < F case with several windows compacts rows at the end)
-  const bool fused = fuse_norm_ok(h, Mll + B) && !shared && s.enc_layers > 0;   // + B: the last conv GEMM carries one junk row per window
+  // RMSNorms in GEMM epilogues.  Few-rows regime: the last conv GEMM itself is the first producer (+ B: it carries one junk
+  // row per window); otherwise one rowstats pass after the conv stack.
+  const int fuse_mode = !(fuse_norm_ok(h, Mll + B) && s.enc_layers > 0) ? 0 : ((h->fuse_norm == 3 && !few_rows_regime(h, Mll + B)) ? 2 : 1);
+  const bool fused = fuse_mode == 1;
+  const bool conv_producer = fused && few_rows_regime(h, Mll + B) && !shared;
 
   // ---- carve workspace (sizes first, then pointers)
   Carver cv;
@@ -597,17 +624,18 @@ int encode_impl(mc_handle* h, const float* wav, int64_t ld, int B, int T, int ke
               reinterpret_cast<float4*>(sb.x), B, F, pre, (int)(ld / hop), d / 4);
     MC_LAUNCH_CHECK(h, "gather_stem_kernel");
   } else {
-    if (fused)
+    if (conv_producer)
       MC_TRY(run_conv_stack(h, cp_full, base, wav, ld, T, sb.x, (int64_t)F * d, stream, sb.hbuf, h->ptr<float>("enc.layers.0.norm1"), sb.stats));
     else
       MC_TRY(run_conv_stack(h, cp_full, base, wav, ld, T, sb.x, (int64_t)F * d, stream));
   }
+  if (fused && !conv_producer) MC_TRY(launch_rowstats(h, sb.x, h->ptr<float>("enc.layers.0.norm1"), sb.hbuf, sb.stats, M, d, stream));
   // ---- transformer (only the rows the kept frames depend on, unless the full latents are requested)
   const int keep_rows = z_e_out ? F : keep;
   float* xk = nullptr;
   bf16* xbk = sb.hbuf;
   float* stk = nullptr;
-  MC_TRY(run_layers(h, "enc", s.enc_layers, sb, B, F, keep_rows, &xk, stream, fused, fused ? h->ptr<float>("enc.norm_f") : nullptr, &xbk, &stk));
+  MC_TRY(run_layers(h, "enc", s.enc_layers, sb, B, F, keep_rows, &xk, stream, fuse_mode, fused ? h->ptr<float>("enc.norm_f") : nullptr, &xbk, &stk));
   const int Mk = B * keep_rows;
   if (!fused) MC_TRY(launch_rmsnorm(h, xk, h->ptr<float>("enc.norm_f"), sb.hbuf, Mk, d, INT_MAX, 0, 0, stream));
   GemmCall pj{};
@@ -672,11 +700,14 @@ int decode_impl(mc_handle* h, const int64_t* codes, const float* z_q, int B, int
   GemmCall ip{};
   ip.A = a0; ip.a_rows = M; ip.a_k_wrap = 64; ip.W = h->ptr<bf16>("dec.in_proj.w"); ip.bias = h->ptr<float>("dec.in_proj.b");
   ip.M = M; ip.N = d; ip.K = 64; ip.act = ACT_NONE; ip.out_mode = OUT_F32; ip.out = sb.x; ip.ldo = d;
-  const bool fused = fuse_norm_ok(h, Mll) && s.dec_layers > 0;
-  if (fused) { ip.xb_out = sb.hbuf; ip.xb_gamma = h->ptr<float>("dec.layers.0.norm1"); ip.stat_out = sb.stats; }
+  const int fuse_mode = !(fuse_norm_ok(h, Mll) && s.dec_layers > 0) ? 0 : ((h->fuse_norm == 3 && !few_rows_regime(h, Mll)) ? 2 : 1);
+  const bool fused = fuse_mode == 1;
+  const bool proj_producer = fused && few_rows_regime(h, Mll);
+  if (proj_producer) { ip.xb_out = sb.hbuf; ip.xb_gamma = h->ptr<float>("dec.layers.0.norm1"); ip.stat_out = sb.stats; }
   MC_TRY(launch_gemm(h, ip, stream));
+  if (fused && !proj_producer) MC_TRY(launch_rowstats(h, sb.x, h->ptr<float>("dec.layers.0.norm1"), sb.hbuf, sb.stats, M, d, stream));
   float* xk = nullptr;
-  MC_TRY(run_layers(h, "dec", s.dec_layers, sb, B, F, Rk, &xk, stream, fused));
+  MC_TRY(run_layers(h, "dec", s.dec_layers, sb, B, F, Rk, &xk, stream, fuse_mode));
 
   {  // zero row 0 (left pad) of every transposed-conv input (one launch)
     PadList pl;
@@ -986,7 +1017,10 @@ int mc_set_option(mc_handle* h, const char* key, int32_t value) {
   else if (k == "attn_p_tmem") h->attn_p_tmem = value != 0;
   else if (k == "debug_repeat") h->debug_repeat = value;   // mc_op_* launch their kernel `value` times back to back (timing tools)
   else if (k == "l2_prefetch") { h->l2_prefetch = value != 0; h->tensor_gen++; }
-  else if (k == "fuse_norm") { h->fuse_norm = value != 0; h->tensor_gen++; }
+  else if (k == "fuse_norm") {
+    if (value < 0 || value > 3) return h->fail(MC_ERR_ARG, "mc_set_option: fuse_norm is 0 .. 3");
+    h->fuse_norm = value; h->tensor_gen++;
+  }
   else if (k == "small_m_split_k") {   // 0 never, 1 streaming sessions only (default), 2 every GEMM of <= 256 rows
     if (value < 0 || value > 2) return h->fail(MC_ERR_ARG, "mc_set_option: small_m_split_k is 0, 1 or 2");
     h->split_k = value;
@@ -1023,6 +1057,29 @@ int mc_op_gemm(mc_handle* h, const void* A, int64_t a_rows, int32_t a_k_wrap, co
   g.rope_cols = rope_cols; g.rope_period = rope_period; g.block_n = block_n;
   for (int r = 1; r < h->debug_repeat; ++r) MC_TRY(launch_gemm(h, g, (cudaStream_t)stream));   // back-to-back chain (timing)
   return launch_gemm(h, g, (cudaStream_t)stream);
+}
+
+/* Plain GEMM with the fused-RMSNorm roles (GemmParams): consumer (row_stats [M, row_stats_n] -> y = acc * rs(row) + bias)
+ * and / or producer (fp32 output modes: also xb_out = bf16(x_new * xb_gamma) [M, N] and stat_out [M, N/64]). */
+int mc_op_gemm_fused(mc_handle* h, const void* A, const void* W, const float* bias, int32_t M, int32_t N, int32_t K, int32_t act,
+                     int32_t out_mode, void* out, const float* row_stats, int32_t row_stats_n, void* xb_out, const float* xb_gamma,
+                     float* stat_out, int32_t rope_cols, int32_t rope_period, int32_t block_n, mc_stream_t stream) {
+  MC_ENTER(h);
+  GemmCall g{};
+  g.A = reinterpret_cast<const bf16*>(A); g.a_rows = M; g.a_k_wrap = K;
+  g.W = reinterpret_cast<const bf16*>(W); g.bias = bias; g.M = M; g.N = N; g.K = K; g.act = act; g.out_mode = out_mode;
+  g.out = out; g.ldo = N;
+  g.rope_cols = rope_cols; g.rope_period = rope_period; g.block_n = block_n;
+  g.row_stats = row_stats; g.row_stats_n = row_stats_n;
+  g.xb_out = reinterpret_cast<bf16*>(xb_out); g.xb_gamma = xb_gamma; g.stat_out = stat_out;
+  return launch_gemm(h, g, (cudaStream_t)stream);
+}
+
+int mc_op_rowstats(mc_handle* h, const float* x, const float* gamma, void* xb_out, float* stat_out, int32_t M, int32_t d,
+                   mc_stream_t stream) {
+  MC_ENTER(h);
+  if (!x || !gamma || !xb_out || !stat_out || M < 1 || d % 64 != 0) return h->fail(MC_ERR_ARG, "mc_op_rowstats: bad arguments");
+  return launch_rowstats(h, x, gamma, reinterpret_cast<bf16*>(xb_out), stat_out, M, d, (cudaStream_t)stream);
 }
 
 int mc_op_rmsnorm(mc_handle* h, const float* x, const float* gamma, void* out_bf16, int32_t M, int32_t d,

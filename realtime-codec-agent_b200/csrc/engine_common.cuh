@@ -69,7 +69,7 @@ struct mc_handle {
   int split_k = 1;
   bool in_session = false;
   int debug_repeat = 1;
-  bool fuse_norm = true;      // few-rows path: RMSNorms live in the epilogues of the GEMMs around them (no rmsnorm launches)
+  int fuse_norm = 1;          // RMSNorms in the epilogues of the GEMMs around them: 0 never, 1 few-rows path, 2 / 3 also offline
   bool l2_prefetch = true;    // split-K GEMMs pull the next GEMM's weights into L2 while they run
   bool pdl = true;            // programmatic dependent launch between consecutive kernels of a pass
   bool shared_stem = true;  // overlapping hop-aligned windows share one pass of the conv stack (exact)

@@ -168,11 +168,16 @@ __device__ __forceinline__ void gemm_epilogue_slab(const GemmParams& p, const CU
       v[j] = __uint_as_float(raw0[j]);
       v[32 + j] = __uint_as_float(raw1[j]);
     }
-    if (p.row_stats != nullptr) {
+    // fused-RMSNorm consumer: ONE expression in every kernel (fmaf(acc, rs, bias)) so that results do not depend on
+    // which kernel a batch size selects
+    if (p.row_stats != nullptr && has_bias) {
 #pragma unroll
-      for (int j = 0; j < 64; ++j) v[j] *= rs;
-    }
-    if (has_bias) {
+      for (int j = 0; j < 64; ++j) v[j] = fmaf(v[j], rs, st.bias[j]);
+      if (c + 1 < BN / 64 && n0 + 64 < p.N) epi_load_bias<BN>(p, n0 + 64, st.bias);
+    } else if (p.row_stats != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) v[j] = __fmul_rn(v[j], rs);
+    } else if (has_bias) {
 #pragma unroll
       for (int j = 0; j < 64; ++j) v[j] += st.bias[j];
       if (c + 1 < BN / 64 && n0 + 64 < p.N) epi_load_bias<BN>(p, n0 + 64, st.bias);  // next chunk, in flight during this one
@@ -272,7 +277,7 @@ __device__ __forceinline__ void gemm_epilogue_slab(const GemmParams& p, const CU
             for (int j = 0; j < 64; j += 4) {
               if (n0 + j < p.N) {
                 const float4 a = *reinterpret_cast<const float4*>(o + j);
-                v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
+                v[j] = __fadd_rn(v[j], a.x); v[j + 1] = __fadd_rn(v[j + 1], a.y); v[j + 2] = __fadd_rn(v[j + 2], a.z); v[j + 3] = __fadd_rn(v[j + 3], a.w);
               }
             }
           }
@@ -285,10 +290,10 @@ __device__ __forceinline__ void gemm_epilogue_slab(const GemmParams& p, const CU
 #pragma unroll
               for (int e = 0; e < 8; ++e) ss = fmaf(v[j + e], v[j + e], ss);
               uint4 w;
-              w.x = pack_bf16x2(v[j] * gam[j], v[j + 1] * gam[j + 1]);
-              w.y = pack_bf16x2(v[j + 2] * gam[j + 2], v[j + 3] * gam[j + 3]);
-              w.z = pack_bf16x2(v[j + 4] * gam[j + 4], v[j + 5] * gam[j + 5]);
-              w.w = pack_bf16x2(v[j + 6] * gam[j + 6], v[j + 7] * gam[j + 7]);
+              w.x = pack_bf16x2(__fmul_rn(v[j], gam[j]), __fmul_rn(v[j + 1], gam[j + 1]));
+              w.y = pack_bf16x2(__fmul_rn(v[j + 2], gam[j + 2]), __fmul_rn(v[j + 3], gam[j + 3]));
+              w.z = pack_bf16x2(__fmul_rn(v[j + 4], gam[j + 4]), __fmul_rn(v[j + 5], gam[j + 5]));
+              w.w = pack_bf16x2(__fmul_rn(v[j + 6], gam[j + 6]), __fmul_rn(v[j + 7], gam[j + 7]));
               *reinterpret_cast<uint4*>(xb + j) = w;
             }
           }
@@ -329,7 +334,7 @@ __device__ __forceinline__ void gemm_epilogue_slab(const GemmParams& p, const CU
 //     tcgen05.ld.x32 + wait, none of it overlapped).
 // Requirements (checked by the launcher): TMA-store output, bias present, N a multiple of BN.
 // ---------------------------------------------------------------------------------------------
-enum : int { EPI_GENERIC = 0, EPI_ROPE_BF16 = 1, EPI_GELU_BF16 = 2, EPI_RESID_F32 = 3 };
+enum : int { EPI_GENERIC = 0, EPI_ROPE_BF16 = 1, EPI_GELU_BF16 = 2, EPI_RESID_F32 = 3, EPI_RESID_NORM = 4 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -350,6 +355,8 @@ struct EpiFastRegs {
   float rc[32], rs[32];    // RoPE variant only (dead otherwise)
   int rope_pos = -1;
   int buf_sel = 0;
+  float row_scale = 1.0f;  // fused-RMSNorm consumer: rs of this thread's row for the current tile
+  uint32_t xphase = 0;     // EPI_RESID_NORM: parity bits of the two x_old staging barriers
 };
 
 __device__ __forceinline__ float4 lds_f4(const float* smem_ptr) {
@@ -376,11 +383,24 @@ __device__ __forceinline__ void epi_fast_chunk(const GemmParams& p, const CUtens
   // load was sunk below all 64 activations and its latency overlapped only the 8 shared-memory stores).
   if (p.one != 0) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b0 = lds_f4(sb + j);
-      const float4 b1 = lds_f4(sb + 32 + j);
-      v[j] += b0.x; v[j + 1] += b0.y; v[j + 2] += b0.z; v[j + 3] += b0.w;
-      v[32 + j] += b1.x; v[32 + j + 1] += b1.y; v[32 + j + 2] += b1.z; v[32 + j + 3] += b1.w;
+    if (p.row_stats != nullptr) {     // fused-RMSNorm consumer (uniform): fmaf(acc, rs, bias), the expression of every kernel
+      const float rsc = st.row_scale;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b0 = lds_f4(sb + j);
+        const float4 b1 = lds_f4(sb + 32 + j);
+        v[j] = fmaf(v[j], rsc, b0.x); v[j + 1] = fmaf(v[j + 1], rsc, b0.y); v[j + 2] = fmaf(v[j + 2], rsc, b0.z); v[j + 3] = fmaf(v[j + 3], rsc, b0.w);
+        v[32 + j] = fmaf(v[32 + j], rsc, b1.x); v[32 + j + 1] = fmaf(v[32 + j + 1], rsc, b1.y);
+        v[32 + j + 2] = fmaf(v[32 + j + 2], rsc, b1.z); v[32 + j + 3] = fmaf(v[32 + j + 3], rsc, b1.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b0 = lds_f4(sb + j);
+        const float4 b1 = lds_f4(sb + 32 + j);
+        v[j] += b0.x; v[j + 1] += b0.y; v[j + 2] += b0.z; v[j + 3] += b0.w;
+        v[32 + j] += b1.x; v[32 + j + 1] += b1.y; v[32 + j + 2] += b1.z; v[32 + j + 3] += b1.w;
+      }
     }
     if (EPI == EPI_GELU_BF16) {
 #pragma unroll
@@ -457,6 +477,10 @@ __device__ __forceinline__ void gemm_epilogue_slab_fast(const GemmParams& p, con
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(sbias + i * (BN / 128) + u)), "f"(bv) : "memory");
     }
   }
+  if (p.row_stats != nullptr) {
+    const int g = row_base + q * 32 + lane;
+    st.row_scale = g < p.M ? row_rs(p, g) : 1.0f;
+  }
   if (EPI == EPI_ROPE_BF16) {
     if (n_base < p.rope_cols) {
       const int g = row_base + q * 32 + lane;
@@ -507,6 +531,129 @@ __device__ __forceinline__ void gemm_epilogue_slab_fast(const GemmParams& p, con
       reg_fence32(a_lo);
       reg_fence32(a_hi);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// EPI_RESID_NORM: the residual GEMMs (Wo, W2) as PRODUCERS of the next RMSNorm (offline path).  The plain residual
+// epilogue adds into x with cp.reduce.async.bulk and never sees x; here the old residual tile comes IN through TMA
+// (fp32 boxes of 32 x 32, two per 64-column chunk, double-buffered per epilogue warp), the thread forms
+// x_new = (acc + bias) + x_old for its row, accumulates the chunk's sum of squares, writes x_new back IN PLACE and
+// bf16(x_new * gamma) beside it, and both leave through TMA stores; stat_out[row][N/64] gets the chunk sum.  The
+// consumer GEMM (QKV / W1) then reads bf16(x * gamma) as its A operand and scales its accumulator rows by
+// rsqrt(sum / d + eps): the 110 us / 629 MB rmsnorm pass between the two GEMMs disappears.  Arithmetic is expression
+// for expression that of gemm_epilogue_slab's producer branch (tested bit-identical), so results do not depend on which
+// kernel a batch size selects.  The epilogue of tile i runs under the main loop of tile i+1 (two TMEM accumulators), so
+// its TMA round trips are hidden as long as it is shorter than a main loop (Wo: ~9 us per tile, W2: ~17 us).
+// Shared memory per warp: 4 x 4 KB x_old / x_new boxes + one 4 KB bf16 box; the kernel runs 4 pipeline stages.
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_slab_resid_norm(const GemmParams& p, const CUtensorMap* map_x, const CUtensorMap* map_xb,
+                                                              uint32_t tmem_acc, int row_base, int n_base, int q, int lane,
+                                                              uint8_t* wbuf /*20 KB of this warp*/, uint64_t* xbar /*[2] of this warp*/,
+                                                              float* sbias /*[2*BN]: bias | gamma*/, EpiFastRegs& st,
+                                                              uint64_t* ready_bar, uint32_t ready_parity) {
+  static_assert(BN % 128 == 0, "chunk pairs");
+  named_bar_sync(1, 128);
+  {
+    const int i = q * 32 + lane;
+#pragma unroll
+    for (int u = 0; u < BN / 128; ++u) {
+      const int n = i * (BN / 128) + u;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(sbias + n)), "f"(__ldg(p.bias + n_base + n)) : "memory");
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(sbias + BN + n)), "f"(__ldg(p.xb_gamma + n_base + n)) : "memory");
+    }
+  }
+  const int row0 = row_base + q * 32;
+  const int g = row0 + lane;
+  uint8_t* xb0 = wbuf;                    // x boxes: [set][half] 4 KB each
+  uint8_t* bf0 = wbuf + 4 * kEpiBufBytes; // one bf16 box
+  if (lane == 0) {
+    tma_wait_group_read<0>();             // the previous tile's stores have been read out of these buffers
+#pragma unroll
+    for (int set = 0; set < 2; ++set) {
+      mbar_arrive_expect_tx(&xbar[set], 2 * kEpiBufBytes);
+      tma_load_2d(xb0 + (set * 2) * kEpiBufBytes, map_x, &xbar[set], n_base + set * 64, row0);
+      tma_load_2d(xb0 + (set * 2 + 1) * kEpiBufBytes, map_x, &xbar[set], n_base + set * 64 + 32, row0);
+    }
+  }
+  named_bar_sync(1, 128);
+  mbar_wait(ready_bar, ready_parity);     // accumulator complete
+  tc_fence_after();
+  const uint32_t tbase = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+  const int sw = lane & 7;
+  const int nst = p.N >> 6;
+#pragma unroll 1
+  for (int c = 0; c < BN / 64; ++c) {
+    const int set = c & 1;
+    const int n0 = n_base + c * 64;
+    uint32_t lo[32], hi[32];
+    tmem_ld_32x32b_x32(tbase + c * 64, lo);
+    tmem_ld_32x32b_x32(tbase + c * 64 + 32, hi);
+    tmem_ld_wait();
+    mbar_wait(&xbar[set], (st.xphase >> set) & 1u);
+    st.xphase ^= (1u << set);
+    float v[64];
+    const float* sb = sbias + c * 64;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      uint8_t* xbox = xb0 + (set * 2 + hf) * kEpiBufBytes + lane * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 xo = lds_f4(reinterpret_cast<const float*>(xbox + ((j ^ sw) << 4)));
+        const float4 bb = lds_f4(sb + hf * 32 + 4 * j);
+        const uint32_t* a = (hf == 0 ? lo : hi) + 4 * j;
+        float* vv = v + hf * 32 + 4 * j;
+        vv[0] = __fadd_rn(__fadd_rn(__uint_as_float(a[0]), bb.x), xo.x);
+        vv[1] = __fadd_rn(__fadd_rn(__uint_as_float(a[1]), bb.y), xo.y);
+        vv[2] = __fadd_rn(__fadd_rn(__uint_as_float(a[2]), bb.z), xo.z);
+        vv[3] = __fadd_rn(__fadd_rn(__uint_as_float(a[3]), bb.w), xo.w);
+      }
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) ss = fmaf(v[j], v[j], ss);
+    if (g < p.M) p.stat_out[static_cast<long long>(g) * nst + (n0 >> 6)] = ss;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      uint8_t* xbox = xb0 + (set * 2 + hf) * kEpiBufBytes + lane * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float* vv = v + hf * 32 + 4 * j;
+        sts_u4(xbox + ((j ^ sw) << 4), make_uint4(__float_as_uint(vv[0]), __float_as_uint(vv[1]), __float_as_uint(vv[2]), __float_as_uint(vv[3])));
+      }
+    }
+    if (lane == 0) tma_wait_group_read<0>();   // the previous chunk's bf16 store has left the (single) bf16 box
+    __syncwarp();
+    {
+      uint8_t* bbox = bf0 + lane * 128;
+      const float* sg = sbias + BN + c * 64;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 g0 = lds_f4(sg + 8 * j), g1 = lds_f4(sg + 8 * j + 4);
+        uint4 w;
+        w.x = pack_bf16x2(__fmul_rn(v[8 * j], g0.x), __fmul_rn(v[8 * j + 1], g0.y));
+        w.y = pack_bf16x2(__fmul_rn(v[8 * j + 2], g0.z), __fmul_rn(v[8 * j + 3], g0.w));
+        w.z = pack_bf16x2(__fmul_rn(v[8 * j + 4], g1.x), __fmul_rn(v[8 * j + 5], g1.y));
+        w.w = pack_bf16x2(__fmul_rn(v[8 * j + 6], g1.z), __fmul_rn(v[8 * j + 7], g1.w));
+        sts_u4(bbox + ((j ^ sw) << 4), w);
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(map_x, xb0 + (set * 2) * kEpiBufBytes, n0, row0);
+      tma_store_2d(map_x, xb0 + (set * 2 + 1) * kEpiBufBytes, n0 + 32, row0);
+      tma_store_2d(map_xb, bf0, n0, row0);
+      tma_commit_group();
+      if (c + 2 < BN / 64) {              // this set's next use: chunk c + 2 — its stores must have left the buffers first
+        tma_wait_group_read<0>();
+        mbar_arrive_expect_tx(&xbar[set], 2 * kEpiBufBytes);
+        tma_load_2d(xb0 + (set * 2) * kEpiBufBytes, map_x, &xbar[set], n0 + 128, row0);
+        tma_load_2d(xb0 + (set * 2 + 1) * kEpiBufBytes, map_x, &xbar[set], n0 + 128 + 32, row0);
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -674,16 +821,18 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 //   empty barrier  : per CTA, released by the leader's multicast tcgen05.commit
 //   tmem_full      : per CTA, multicast commit;  tmem_empty: leader's, 8 arrivals (4 warps x 2 CTAs)
 // =============================================================================================
-template <int BN>
+template <int BN, int EPI = EPI_GENERIC>
 struct Gemm2Cfg {
   static constexpr int kStageBytesA = GEMM_BM * GEMM_BK * 2;
   static constexpr int kStageBytesB = (BN / 2) * GEMM_BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = 196608 / kStageBytes;
+  // EPI_RESID_NORM stages the old residual tile through shared memory (6 boxes per epilogue warp): 4 stages instead of 6
+  // (measured: all pair GEMMs at 4 stages lose 1-4 %; only Wo / W2 run this variant)
+  static constexpr int kEpiBytes = (EPI == EPI_RESID_NORM ? 4 * 5 : 4 * 2) * kEpiBufBytes;
+  static constexpr int kStages = (EPI == EPI_RESID_NORM ? 131072 : 196608) / kStageBytes;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kEpiBytes = 4 * 2 * kEpiBufBytes;
   static constexpr int kBarBytes = 256;
-  static constexpr int kBiasBytes = BN * 4;   // per-tile bias staging of the specialised epilogues
+  static constexpr int kBiasBytes = (EPI == EPI_RESID_NORM ? 2 : 1) * BN * 4;   // per-tile bias (and gamma) staging of the specialised epilogues
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + kBiasBytes + 1024;
   static_assert(kSmemBytes <= 232448, "CTA-pair GEMM exceeds 227 KB of shared memory");
 };
@@ -691,8 +840,8 @@ struct Gemm2Cfg {
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                        const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
-  using Cfg = Gemm2Cfg<BN>;
+                        const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out2, const GemmParams p) {
+  using Cfg = Gemm2Cfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_base = smem + Cfg::kStages * Cfg::kStageBytes;
@@ -701,8 +850,9 @@ gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* sbias = reinterpret_cast<float*>(bar_base + Cfg::kBarBytes);   // [BN], fast epilogues only
+  uint64_t* xbar = tmem_empty + 2;                                       // [4 warps][2]: x_old staging of EPI_RESID_NORM
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(xbar + 8);
+  float* sbias = reinterpret_cast<float*>(bar_base + Cfg::kBarBytes);   // [2*BN], fast epilogues only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -717,6 +867,7 @@ gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     if (p.tma_store) tma_prefetch_desc(&map_out);
+    if (EPI == EPI_RESID_NORM) tma_prefetch_desc(&map_out2);
   }
   if (warp == 5 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -727,6 +878,7 @@ gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 8);
     }
+    for (int s = 0; s < 8; ++s) mbar_init(&xbar[s], 1);
     fence_mbar_init();
   }
   if (warp == 6) {
@@ -792,7 +944,7 @@ gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     }
   } else if (warp < 4) {
     const int q = warp;
-    uint8_t* my_bufs = epi_base + q * 2 * kEpiBufBytes;
+    uint8_t* my_bufs = epi_base + q * (EPI == EPI_RESID_NORM ? 5 : 2) * kEpiBufBytes;
     typename std::conditional<EPI == EPI_GENERIC, EpiRegs, EpiFastRegs>::type st;
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
@@ -802,6 +954,9 @@ gemm2_bf16_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       if constexpr (EPI == EPI_GENERIC) {
         gemm_epilogue_slab<BN>(p, &map_out, tmem_base + acc * BN, m_blk * 2 * GEMM_BM + rank * GEMM_BM, n_blk * BN, q, lane,
                                my_bufs, st, &tmem_full[acc], acc_phase);
+      } else if constexpr (EPI == EPI_RESID_NORM) {
+        gemm_epilogue_slab_resid_norm<BN>(p, &map_out, &map_out2, tmem_base + acc * BN, m_blk * 2 * GEMM_BM + rank * GEMM_BM,
+                                          n_blk * BN, q, lane, my_bufs, xbar + 2 * q, sbias, st, &tmem_full[acc], acc_phase);
       } else {
         gemm_epilogue_slab_fast<BN, EPI>(p, &map_out, tmem_base + acc * BN, m_blk * 2 * GEMM_BM + rank * GEMM_BM, n_blk * BN, q,
                                          lane, my_bufs, sbias, st, &tmem_full[acc], acc_phase);

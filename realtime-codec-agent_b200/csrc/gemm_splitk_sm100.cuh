@@ -247,13 +247,12 @@ gemm_splitk_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           v[hf][q * 4] = acc.x; v[hf][q * 4 + 1] = acc.y; v[hf][q * 4 + 2] = acc.z; v[hf][q * 4 + 3] = acc.w;
         }
       }
-      if (p.row_stats != nullptr) {
+      if (p.row_stats != nullptr) {             // fmaf(acc, rs, bias): the consumer expression of every kernel (bias is 0 when absent)
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
-          for (int j = 0; j < kHalf; ++j) v[hf][j] *= e_rs;
-      }
-      if (p.bias != nullptr) {
+          for (int j = 0; j < kHalf; ++j) v[hf][j] = p.bias != nullptr ? fmaf(v[hf][j], e_rs, e_bias[hf][j]) : __fmul_rn(v[hf][j], e_rs);
+      } else if (p.bias != nullptr) {
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf)
 #pragma unroll

@@ -502,6 +502,29 @@ class B200Generator:
         nat.check(self._lib, self._handle, rc, "mc_op_gemm")
         return out
 
+    def op_gemm_fused(self, A, W, bias=None, act=0, out_mode=1, out=None, row_stats=None, xb_gamma=None, rope_cols=0,
+                      rope_period=0, block_n=0):
+        """GEMM with the fused-RMSNorm roles: row_stats [M, n] -> consumer; xb_gamma [N] -> producer (returns out, xb, stats)."""
+        M, K = A.shape
+        N = W.shape[0]
+        if out is None:
+            out = torch.zeros((M, N), dtype=BF16 if out_mode == 0 else F32, device=self.device)
+        xb = torch.zeros((M, N), dtype=BF16, device=self.device) if xb_gamma is not None else None
+        st = torch.zeros((M, N // 64), dtype=F32, device=self.device) if xb_gamma is not None else None
+        rc = self._lib.mc_op_gemm_fused(self._handle, A.data_ptr(), W.data_ptr(), nat.ptr(bias), M, N, K, act, out_mode, out.data_ptr(),
+                                        nat.ptr(row_stats), 0 if row_stats is None else row_stats.shape[1], nat.ptr(xb), nat.ptr(xb_gamma),
+                                        nat.ptr(st), rope_cols, rope_period, block_n, self._stream())
+        nat.check(self._lib, self._handle, rc, "mc_op_gemm_fused")
+        return (out, xb, st) if xb_gamma is not None else out
+
+    def op_rowstats(self, x, gamma):
+        M, d = x.shape
+        xb = torch.empty((M, d), dtype=BF16, device=self.device)
+        st = torch.empty((M, d // 64), dtype=F32, device=self.device)
+        rc = self._lib.mc_op_rowstats(self._handle, x.data_ptr(), gamma.data_ptr(), xb.data_ptr(), st.data_ptr(), M, d, self._stream())
+        nat.check(self._lib, self._handle, rc, "mc_op_rowstats")
+        return xb, st
+
     def op_emit_chunk(self, wav, chunk, fade, has_prev, target_rms, silence_thr, fade_in, prev_tail):
         out = torch.empty((2 * chunk + fade,), dtype=F32, device=self.device)
         rc = self._lib.mc_op_emit_chunk(self._handle, wav.data_ptr(), wav.numel(), chunk, fade, int(has_prev), float(target_rms),

@@ -224,6 +224,77 @@ def test_splitk_gemm_conv_view_and_auto_selection(gen):
         gen.set_option("small_m_split_k", 1)
 
 
+@pytest.mark.parametrize("M", [100, 300, 2560, 25600])
+def test_fused_rmsnorm_producer_and_consumer_kernels_agree_bit_for_bit(gen, M):
+    """RMSNorm folded into the GEMMs around it.  Producer (residual GEMM emitting x_new, bf16(x_new * gamma) and per-row
+    sums of squares per 64 columns): the CTA-pair kernel's TMA epilogue (EPI_RESID_NORM), the generic per-thread epilogue
+    (block_n 64 / 128 / 256), the split-K kernel and the standalone rowstats pass must agree BIT FOR BIT on x, xb and the
+    statistics of every 64-column chunk they share, or results would depend on the batch size.  Consumer (QKV + RoPE, W1 +
+    GELU): fast and generic epilogues bit-identical, and the fused pair of GEMMs equals RMSNorm-then-GEMM in fp32."""
+    N, K = 1024, 1024
+    A = _rand((M, K), seed=61).to(torch.bfloat16)
+    W = (_rand((N, K), seed=62) / math.sqrt(K)).to(torch.bfloat16)
+    bias = _rand((N,), seed=63)
+    gamma = 1.0 + 0.1 * _rand((N,), seed=64)
+    x0 = _rand((M, N), seed=65)
+    outs = {}
+    variants = [("generic64", 64), ("generic128", 128), ("generic256", 256)]
+    if M >= 2560:
+        variants.append(("pair", 512))
+    if M <= 256:
+        variants.append(("splitk8", 1008))
+    for name, bn in variants:
+        x = x0.clone()
+        _, xb, st = gen.op_gemm_fused(A, W, bias=bias, out_mode=2, out=x, xb_gamma=gamma, block_n=bn)
+        outs[name] = (x, xb, st)
+    ref_x = x0 + A.float() @ W.float().t() + bias
+    base = outs["generic64"]
+    assert (base[0] - ref_x).abs().max().item() < 2e-3
+    assert (base[1].float() - ref_x * gamma).abs().max().item() < 0.05
+    assert torch.allclose(base[2].sum(1), ref_x.pow(2).sum(1), rtol=1e-4)
+    for name, (x, xb, st) in outs.items():
+        if name == "splitk8":                                      # other fp32 summation order: close, not identical
+            assert (x - base[0]).abs().max().item() < 1e-4 and torch.allclose(st, base[2], rtol=1e-3)
+            continue
+        assert torch.equal(x, base[0]) and torch.equal(xb, base[1]) and torch.equal(st, base[2]), name
+    xb_rs, st_rs = gen.op_rowstats(base[0], gamma)                 # the standalone first producer, same arithmetic
+    assert torch.equal(xb_rs, base[1]) and torch.equal(st_rs, base[2])
+    # consumers
+    Wc = (_rand((3072, N), seed=66) / math.sqrt(N)).to(torch.bfloat16)
+    bc = _rand((3072,), seed=67)
+    eps = gen.spec.norm_eps
+    normed = (base[0] * torch.rsqrt(base[0].pow(2).mean(-1, keepdim=True) + eps) * gamma)
+    ref_q = normed @ Wc.float().t() + bc
+    res = {}
+    for name, bn in (("generic64", 64), ("generic256", 256)) + ((("pair", 512),) if M >= 2560 else ()) + ((("splitk", 1004),) if M <= 128 else ()):
+        res[name] = gen.op_gemm_fused(base[1], Wc, bias=bc, out_mode=1, row_stats=base[2], block_n=bn)
+    q64 = res["generic64"]
+    assert (q64 - ref_q).abs().max().item() < 0.06                 # bf16(x * gamma) operand vs fp32 normalised operand
+    for name, q in res.items():
+        if name == "splitk":
+            assert (q - q64).abs().max().item() < 1e-3
+        else:
+            assert torch.equal(q, q64), name
+    if M >= 2560:                                                  # fast RoPE / GELU epilogues with the row scale == generic
+        Fr = 100
+        for kw in (dict(out_mode=0, rope_cols=2048, rope_period=Fr), dict(out_mode=0, act=1)):
+            try:
+                gen.set_option("fast_epilogue", 1)
+                fast = gen.op_gemm_fused(base[1], Wc, bias=bc, row_stats=base[2], block_n=512, **kw)
+                gen.set_option("fast_epilogue", 0)
+                slow = gen.op_gemm_fused(base[1], Wc, bias=bc, row_stats=base[2], block_n=512, **kw)
+            finally:
+                gen.set_option("fast_epilogue", 1)
+            assert torch.equal(fast, slow) and torch.equal(fast, gen.op_gemm_fused(base[1], Wc, bias=bc, row_stats=base[2], block_n=64, **kw))
+        try:                                                       # and the TMA producer epilogue == the pair kernel's generic one
+            gen.set_option("fast_epilogue", 0)
+            x = x0.clone()
+            _, xb, st = gen.op_gemm_fused(A, W, bias=bias, out_mode=2, out=x, xb_gamma=gamma, block_n=512)
+        finally:
+            gen.set_option("fast_epilogue", 1)
+        assert torch.equal(x, base[0]) and torch.equal(xb, base[1]) and torch.equal(st, base[2])
+
+
 def test_rmsnorm(gen):
     x = _rand((333, 512), scale=3.0, seed=16)
     g = 1.0 + 0.1 * _rand((512,), seed=17)

@@ -40,7 +40,14 @@ def run(tag, iters=3):
 
 
 codes = run("default")
-if only_default:
+if len(sys.argv) > 2 and sys.argv[2] == "fuse":      # offline RMSNorm fusion variants, same process / same thermal state
+    for rep in range(2):
+        for mode, tag in ((1, "fuse_norm=1 (few-rows only: default)"), (2, "fuse_norm=2 (Wo + W2 produce)"), (3, "fuse_norm=3 (Wo only)")):
+            gen.set_option("fuse_norm", mode)
+            c = run(tag)
+            print("   codes equal to default:", round(float((c == codes).float().mean()), 4))
+    gen.set_option("fuse_norm", 1)
+elif only_default:
     torch.cuda.profiler.start()          # ncu --profile-from-start off captures one warm batch
     run("default", iters=1)
     torch.cuda.profiler.stop()
