@@ -139,7 +139,7 @@ def encode_corpus(gen, audio_path: str, codes_path: str, codec_model: str = "Mag
     # ---- pipeline
     ingest = ingest if ingest is not None else audio_io.DeviceIngest(gen)
     pool = _PinnedPool(prefetch_files + 1, ingest.host_buffer)
-    write_q: "queue.Queue" = queue.Queue()
+    write_q: "queue.Queue" = queue.Queue(maxsize=4 * (prefetch_files + 1))    # a slow disk throttles the encoder, not memory
     lock = threading.Lock()
 
     def load(item):
@@ -190,7 +190,8 @@ def encode_corpus(gen, audio_path: str, codes_path: str, codec_model: str = "Mag
     wt = threading.Thread(target=writer, daemon=True)
     wt.start()
     encoded_secs = 0.0
-    with ThreadPoolExecutor(max(1, loader_threads)) as ex:
+    ex = ThreadPoolExecutor(max(1, loader_threads))
+    try:
         inflight = []
         it = iter(todo)
         for _ in range(prefetch_files + 1):                           # never more tasks in flight than pinned buffers
@@ -221,8 +222,10 @@ def encode_corpus(gen, audio_path: str, codes_path: str, codec_model: str = "Mag
             nxt = next(it, None)
             if nxt is not None:
                 inflight.append(ex.submit(load, nxt))
-    write_q.put(None)
-    wt.join()
+    finally:
+        ex.shutdown(wait=True, cancel_futures=True)
+        write_q.put(None)
+        wt.join()
     if stats is not None:
         stats["encoded_audio_secs"] = stats.get("encoded_audio_secs", 0.0) + encoded_secs
         stats["files_encoded"] = stats.get("files_encoded", 0) + len(todo) - len(errors)

@@ -26,6 +26,11 @@ pytestmark = pytest.mark.gpu
 # margin <= 0.101, 97.8-98.7 % of ALL frames agree, decode SNR 42.6-44.2 dB, max-abs 0.7-0.9 % of peak.
 Z_TOL = 0.06
 EPS_MARGIN = 0.15
+# The streaming sessions' few-rows kernels (cluster split-K, RMSNorms in GEMM epilogues) draw their rounding errors
+# differently: on 10 000 default-spec frames (profiles/r02_parity_sweep_50k_frames.jsonl) 97.7 % of all frames agree and
+# the largest disagreeing margin is 0.152 (batched path: 0.104 on 40 000; the reference's bf16-autocast GPU path: 0.164
+# on 4 800) — the stated epsilon of that path is 0.2.
+EPS_MARGIN_STREAM = 0.20
 NEAR_TIE_MAX = 0.30
 SNR_MIN_DB = 38.0
 WAV_TOL = 0.02
@@ -245,7 +250,8 @@ def test_native_audio_tokenizer_streaming(bundle):
     _report(name, stream_agree_all=round(float((got == ref).mean()), 3), stream_clear_frac=round(float(clear.mean()), 3),
             session_splitk_agree_all=round(float((got_stream == ref).mean()), 3))
     assert np.array_equal(got[clear], ref[clear])
-    assert got_stream.shape == ref.shape and np.array_equal(got_stream[clear], ref[clear])
+    clear_stream = (margin[0].numpy() > EPS_MARGIN_STREAM) & (idx[0].numpy() == ref)
+    assert got_stream.shape == ref.shape and np.array_equal(got_stream[clear_stream], ref[clear_stream])
     tok.reset_context()
     ref_str = "".join(chr(int(c) + tok.unicode_offset) for c in ref)
     pieces = []

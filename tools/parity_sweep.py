@@ -14,18 +14,29 @@ import realtime_codec_agent_b200 as pkg
 from oracle.magicodec_oracle import OracleGenerator
 
 
-def sweep(name, spec, n_windows):
+def sweep(name, spec, n_windows, few_rows=False):
+    """few_rows=True: every window alone through the streaming sessions' kernels (cluster split-K GEMMs, RMSNorms folded
+    into GEMM epilogues; mc_set_option small_m_split_k = 2) instead of one batched launch."""
     torch.set_num_threads(os.cpu_count() or 1)
     w = pkg.init_random_weights(spec, seed=0)
     gen = pkg.B200Generator(spec, w, device="cuda", max_positions=512)
     oracle = OracleGenerator(spec, w)
     wav = torch.stack([pkg.synth_audio(32000, seed=77, file_id=i) for i in range(n_windows)])
-    codes, margin_gpu, z_gpu = gen.encode(wav.cuda(), return_margin=True, return_latents=True)
+    if few_rows:
+        gen.set_option("small_m_split_k", 2)
+        parts = [gen.encode(wav[i:i + 1].cuda(), return_margin=True, return_latents=True) for i in range(n_windows)]
+        codes, margin_gpu, z_gpu = (torch.cat([p[k] for p in parts]) for k in range(3))
+        name += " (few-rows kernels, one window per call)"
+    else:
+        codes, margin_gpu, z_gpu = gen.encode(wav.cuda(), return_margin=True, return_latents=True)
     with torch.no_grad():
         z_ref = oracle.encoder(oracle.pad_audio(wav))
         z_q, idx_ref, margin = oracle.quantizer.inference(z_ref, return_margin=True)
         rec_ref = oracle.decoder(z_q)[:, 0]
-    rec = gen.decode(idx_ref.cuda()).cpu()
+    if few_rows:
+        rec = torch.cat([gen.decode(idx_ref[i:i + 1].cuda()) for i in range(n_windows)]).cpu()
+    else:
+        rec = gen.decode(idx_ref.cuda()).cpu()
     codes = codes.cpu()
     dz = (z_gpu.cpu() - z_ref)
     dis = codes != idx_ref
@@ -45,4 +56,6 @@ def sweep(name, spec, n_windows):
 if __name__ == "__main__":
     sweep("tiny", pkg.TINY_SPEC, 40)
     sweep("mid", pkg.MID_SPEC, 40)
-    sweep("default", pkg.DEFAULT_SPEC, int(sys.argv[1]) if len(sys.argv) > 1 else 24)
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+    sweep("default", pkg.DEFAULT_SPEC, n)
+    sweep("default", pkg.DEFAULT_SPEC, min(n, 100), few_rows=True)
