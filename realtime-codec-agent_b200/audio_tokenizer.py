@@ -91,6 +91,7 @@ class AudioTokenizer:
     def reset_context(self):
         with self._lock:
             self.tokenize_context = np.zeros((self.num_channels, 0), dtype=np.float32)
+            self._ctx_buf = None
             self.detokenize_context = ""
             if getattr(self, "_session", None) is not None:
                 self._session.reset()
@@ -158,9 +159,7 @@ class AudioTokenizer:
         n_new = new.shape[-1]
         C = self.num_channels
         sess = self._stream_session() if self._native else None      # before the context changes: mirrors it from the start
-        joined = np.concatenate((self.tokenize_context, new.reshape(C, -1)), axis=-1)
-        keep = max(n_new, self.context_samples)
-        self.tokenize_context = joined[..., -keep:]          # [-0:] keeps everything, as upstream
+        self._append_context(new.reshape(C, -1))
 
         # chars the caller keeps: int(secs*framerate*C); a zero count slices [-0:] == whole string
         n_chars = int(n_new / self.sampling_rate * self.framerate * C)
@@ -186,6 +185,29 @@ class AudioTokenizer:
         text = self._interleave_chars(per_channel)
         return text[-n_chars:]
 
+    def _append_context(self, new: np.ndarray) -> None:
+        """tokenize_context <- the last max(len(new), context_samples) samples of (tokenize_context ++ new)
+        (audio_tokenizer.py:72-74; [-0:] keeps everything, as upstream).  The reference concatenates and slices — a
+        128 KB copy per 20 ms frame; here the context is a view that slides through a buffer of a few context lengths
+        and is moved back to its start only when it reaches the end."""
+        C, n_new = new.shape
+        old = self.tokenize_context
+        keep = max(n_new, self.context_samples)
+        keep_old = min(old.shape[-1], keep - n_new) if n_new < keep else 0
+        buf = getattr(self, "_ctx_buf", None)
+        base = old.base if old.base is not None else old
+        if buf is None or base is not buf or buf.shape[0] != C or keep > buf.shape[1] // 4:
+            buf = np.empty((C, 8 * max(keep, self.context_samples)), dtype=np.float32)
+            buf[:, :keep_old] = old[:, old.shape[-1] - keep_old:]
+            self._ctx_buf, self._ctx_end = buf, keep_old
+        elif self._ctx_end + n_new > buf.shape[1]:
+            buf[:, :keep_old] = old[:, old.shape[-1] - keep_old:]              # regions cannot overlap: keep_old <= size / 8
+            self._ctx_end = keep_old
+        end = self._ctx_end
+        buf[:, end:end + n_new] = new
+        self._ctx_end = end + n_new
+        self.tokenize_context = buf[:, self._ctx_end - keep_old - n_new:self._ctx_end]
+
     def _interleave_chars(self, codes_c1f: np.ndarray) -> str:
         """[C,1,F] codes -> 'c0[0] c1[0] c0[1] c1[1] ...' (audio_tokenizer.py:89-96)."""
         C = codes_c1f.shape[0]
@@ -209,16 +231,17 @@ class AudioTokenizer:
         keep = max(len(audio_codes_str), self.context_frames)
         self.detokenize_context = self.detokenize_context[-keep:]
 
-        flat = chars_to_codes(self.detokenize_context, 1, self.codebook_size, unicode_offset=self.unicode_offset)[0]
-        codes = np.ascontiguousarray(flat.reshape(-1, C).T)                  # [C,F] de-interleave (:116)
-
         want = int(self.get_audio_codes_str_secs(audio_codes_str) * self.sampling_rate) + preroll_samples
+        n_new_frames = len(audio_codes_str) // C
+        on_session = self._native and self._session_codes_ok and 0 < n_new_frames <= sess.cap_frames
+        # de-interleave (:116); on the session path only the NEW codes cross to the device, so only they are converted
+        text = audio_codes_str if on_session else self.detokenize_context
+        flat = chars_to_codes(text, 1, self.codebook_size, unicode_offset=self.unicode_offset)[0]
+        codes = np.ascontiguousarray(flat.reshape(-1, C).T)                  # [C,F]
 
         if self._native:
-            n_new_frames = len(audio_codes_str) // C
-            if self._session_codes_ok and 0 < n_new_frames <= sess.cap_frames:
-                new_codes = codes[:, codes.shape[1] - n_new_frames:]
-                wav = torch.from_numpy(sess.push_codes(new_codes, want))[None]      # [1,C,Tk]
+            if on_session:
+                wav = torch.from_numpy(sess.push_codes(codes, want))[None]          # [1,C,Tk]
             else:
                 dev_codes = torch.from_numpy(codes).to(self.device, non_blocking=True)
                 wav = self.codec_model.decode(dev_codes, keep_last_samples=want)[None].cpu()   # [1,C,Tk] fp32

@@ -14,7 +14,7 @@ import realtime_codec_agent_b200 as pkg
 from oracle.magicodec_oracle import OracleGenerator
 
 
-def sweep(name, spec, n_windows, few_rows=False):
+def sweep(name, spec, n_windows, few_rows=False, fuse_norm=1):
     """few_rows=True: every window alone through the streaming sessions' kernels (cluster split-K GEMMs, RMSNorms folded
     into GEMM epilogues; mc_set_option small_m_split_k = 2) instead of one batched launch."""
     torch.set_num_threads(os.cpu_count() or 1)
@@ -24,6 +24,8 @@ def sweep(name, spec, n_windows, few_rows=False):
     wav = torch.stack([pkg.synth_audio(32000, seed=77, file_id=i) for i in range(n_windows)])
     if few_rows:
         gen.set_option("small_m_split_k", 2)
+        gen.set_option("fuse_norm", fuse_norm)
+        name += f" [fuse_norm={fuse_norm}]"
         parts = [gen.encode(wav[i:i + 1].cuda(), return_margin=True, return_latents=True) for i in range(n_windows)]
         codes, margin_gpu, z_gpu = (torch.cat([p[k] for p in parts]) for k in range(3))
         name += " (few-rows kernels, one window per call)"
@@ -59,3 +61,6 @@ if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 24
     sweep("default", pkg.DEFAULT_SPEC, n)
     sweep("default", pkg.DEFAULT_SPEC, min(n, 100), few_rows=True)
+    if "ablate" in sys.argv:
+        sweep("default", pkg.DEFAULT_SPEC, min(n, 100), few_rows=True, fuse_norm=0)      # split-K kernels, standalone rmsnorm
+        sweep("default", pkg.DEFAULT_SPEC, min(n, 100))                                   # the same 100 windows, batched path
