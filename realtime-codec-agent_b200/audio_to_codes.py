@@ -155,10 +155,11 @@ def encode_corpus(gen, audio_path: str, codes_path: str, codec_model: str = "Mag
             if holder["buf"] is None:                                # zero-length payload never called alloc
                 holder["buf"] = pool.acquire(1)
             return item, pcm, holder["buf"], None
-        except UnsupportedAudio as ex_:
-            if holder["buf"] is None:
+        except Exception as ex_:                                      # noqa: BLE001  (corrupt / unreadable / unsupported:
+            if holder["buf"] is None:                                # the file goes to errors.json, the run goes on)
                 holder["buf"] = pool.acquire(1)
-            return item, None, holder["buf"], str(ex_)
+            msg = str(ex_) if isinstance(ex_, UnsupportedAudio) else f"{files[fid]}: {ex_!r}"
+            return item, None, holder["buf"], msg
 
     def writer():
         while True:
@@ -166,9 +167,9 @@ def encode_corpus(gen, audio_path: str, codes_path: str, codec_model: str = "Mag
             if job is None:
                 return
             fid, rel, dsts, host_codes, wait, n_windows = job
+            tmps = []
             try:
                 wait()
-                tmps = []
                 entries = []
                 for c, dst in enumerate(dsts):
                     arr = host_codes[c].numpy().astype(np.int32)[None, :]   # (num_codebooks=1, T) int32
@@ -184,6 +185,11 @@ def encode_corpus(gen, audio_path: str, codes_path: str, codec_model: str = "Mag
                 with lock:
                     manifest.extend(entries)
             except Exception as ex_:                                  # noqa: BLE001
+                for tmp, _ in tmps:
+                    try:
+                        os.remove(tmp)
+                    except OSError:
+                        pass
                 with lock:
                     errors.append({"file": files[fid], "error": f"write failed: {ex_!r}"})
 
@@ -204,7 +210,8 @@ def encode_corpus(gen, audio_path: str, codes_path: str, codec_model: str = "Mag
             if err is None and pcm.frames == 0:
                 err = f"{files[fid]}: empty audio"
             if err is not None:
-                errors.append({"file": files[fid], "error": err})
+                with lock:
+                    errors.append({"file": files[fid], "error": err})
                 pool.release(buf)
             else:
                 staged = ingest.upload(pcm, buf)                       # copy stream: under the previous file's encode

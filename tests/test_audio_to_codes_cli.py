@@ -110,6 +110,20 @@ def test_mixed_corpus_formats_and_per_file_errors(tmp_path):
     gen = OracleBackedGen(OracleGenerator(pkg.TINY_SPEC, pkg.init_random_weights(pkg.TINY_SPEC, seed=0)))
     man, errs = audio_to_codes.encode_corpus(gen, str(raw), str(tmp_path / "codes"), stereo=True, batch_size=16, ingest=HostIngest(gen))
     assert len(errs) == 1 and errs[0]["file"].endswith("broken.mp3") and "no decoder" in errs[0]["error"]
+    # corrupt inputs of the formats that ARE decoded here: a wav cut inside its fmt chunk, a FLAC with a flipped byte
+    # (frame CRC) and an .npy that is not an array — one errors.json line each, nothing else changes
+    bad = tmp_path / "bad"
+    bad.mkdir()
+    good_wav = (raw / "libri" / "clip.wav").read_bytes()
+    (bad / "cut.wav").write_bytes(good_wav[:30])
+    fl = bytearray((raw / "libri" / "book.flac").read_bytes())
+    fl[len(fl) // 2] ^= 0x5A
+    (bad / "flip.flac").write_bytes(bytes(fl))
+    (bad / "junk.npy").write_bytes(b"not a numpy file")
+    (bad / "ok.wav").write_bytes(good_wav)
+    man_b, errs_b = audio_to_codes.encode_corpus(gen, str(bad), str(tmp_path / "codes_bad"), batch_size=16, ingest=HostIngest(gen))
+    assert sorted(os.path.basename(e["file"]) for e in errs_b) == ["cut.wav", "flip.flac", "junk.npy"]
+    assert [e.path for e in man_b] == ["ok"]
     out = tmp_path / "codes" / "MagiCodec-50Hz-Base" / "0.1s_2.0s" / "stereo"
     assert np.load(out / "fisher/fe_03_00001_c0.npy").shape == (1, 75)            # 1.5 s at 8 kHz -> 24 000 samples at 16 kHz
     assert np.load(out / "fisher/fe_03_00001_c1.npy").shape == (1, 75)
