@@ -42,6 +42,9 @@ __device__ __forceinline__ uint32_t elect_one() {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #ifndef MC_TRACE
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#define MC_TRACE_DECL
+#define MC_TRACE_MARK(ph)
+#define MC_TRACE_FLUSH
 #else
 // Timeline build (python -m realtime_codec_agent_b200.build --trace; tools/trace_stream.py): thread 0 of every CTA logs
 // the global timer before and after its griddepcontrol.wait.  "after" of kernel i+1 minus "after" of kernel i is kernel
@@ -69,6 +72,32 @@ __device__ __forceinline__ void pdl_wait() {
     }
   } else {
     asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
+}
+// phase marks inside a kernel (thread 0 of CTA 0): timestamps are kept in registers and written by mc_trace_flush at the
+// end of the kernel (an atomic per mark would put an L2 round trip into the interval being measured); records carry
+// "block size" 100000 + phase
+struct McTraceMarks {
+  unsigned long long t[16];
+  unsigned int mask = 0;
+};
+#define MC_TRACE_DECL McTraceMarks mc_tm_
+#define MC_TRACE_MARK(ph) do { if (threadIdx.x == 0 && blockIdx.x == 0) { mc_tm_.t[ph] = mc_globaltimer(); mc_tm_.mask |= 1u << (ph); } } while (0)
+#define MC_TRACE_FLUSH mc_trace_flush(mc_tm_)
+__device__ __forceinline__ void mc_trace_flush(const McTraceMarks& m) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && g_mc_trace != nullptr) {
+#pragma unroll
+    for (int ph = 0; ph < 16; ++ph) {
+      if (!(m.mask & (1u << ph))) continue;
+      const unsigned int slot = atomicAdd(&g_mc_trace_n, 1u);
+      if (slot < g_mc_trace_cap) {
+        unsigned long long* r = g_mc_trace + 4ull * slot;
+        r[0] = static_cast<unsigned long long>(gridDim.x) << 32;
+        r[1] = 100000u + ph;
+        r[2] = m.t[ph];
+        r[3] = m.t[ph];
+      }
+    }
   }
 }
 #endif

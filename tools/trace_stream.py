@@ -37,6 +37,9 @@ else:
     sess.push_audio(w[None, 130 * 320:131 * 320], 1)
 n = gen._lib.mc_debug_trace(gen._handle, None, 0)
 rec = buf.cpu().numpy().astype(np.uint64).reshape(-1, 4)[:n]
+marks = rec[rec[:, 1] >= np.uint64(100000)]                 # phase marks of instrumented kernels (mc_trace_mark)
+rec = rec[rec[:, 1] < np.uint64(100000)]
+n = len(rec)
 grid = (rec[:, 0] >> np.uint64(32)).astype(np.int64)
 blk = (rec[:, 0] & np.uint64(0xFFFFFFFF)).astype(np.int64)
 bdim = rec[:, 1].astype(np.int64)
@@ -62,3 +65,25 @@ for k, L in enumerate(launches):
 for j, r in enumerate(rows):
     step = rows[j + 1][4] - r[4] if j + 1 < len(rows) else float("nan")
     print(f"{r[0]:3d} {r[1]:5d} {r[2]:7d} {r[3]:9.2f} {r[4]:11.2f} {r[5]:17.2f} {step:8.2f}")
+
+if len(marks):
+    # phase marks (thread 0 of CTA 0): time since that CTA's dependency resolved, for each instrumented launch
+    mt = marks[:, 2].astype(np.int64)
+    mp = (marks[:, 1].astype(np.int64) - 100000)
+    mg = (marks[:, 0] >> np.uint64(32)).astype(np.int64)
+    res0 = {}
+    for i in range(len(rec)):
+        if blk[i] == 0:
+            res0.setdefault(int(grid[i]), []).append(int(t1[i]))
+    print("# phase marks: us after CTA 0's griddepcontrol.wait returned (one line per instrumented launch)")
+    order = np.argsort(mt, kind="stable")
+    line, prev_t = [], None
+    for i in order:
+        if prev_t is not None and mt[i] - prev_t > 20000 and line:      # > 20 us apart: the next instrumented launch
+            print("  " + "  ".join(line)); line = []
+        cands = [t for t in res0.get(int(mg[i]), []) if t <= mt[i]]
+        ref = max(cands) if cands else mt[i]
+        line.append(f"{mp[i]}:{(mt[i] - ref) / 1e3:.2f}")
+        prev_t = mt[i]
+    if line:
+        print("  " + "  ".join(line))
