@@ -142,7 +142,9 @@ class SessionBatcher:
         with self._lock:
             groups: Dict[Tuple[int, int], List[int]] = {}
             prepped = {}
-            for sid, chunk in chunks.items():
+            for sid, chunk in chunks.items():                    # validate everything before any state changes
+                if sid not in self._sessions:
+                    raise KeyError(f"unknown session {sid}")
                 x = np.asarray(chunk)
                 if x.dtype == np.int16:
                     x = x.astype("float32") / 32768.0
@@ -174,24 +176,27 @@ class SessionBatcher:
         C_ = self.num_channels
         with self._lock:
             groups: Dict[Tuple[int, int], List[int]] = {}
-            new_codes, hanging, wants = {}, {}, {}
-            for sid, s in strings.items():
-                st = self._sessions[sid]
+            new_codes, hanging, wants, trimmed = {}, {}, {}, {}
+            for sid, s in strings.items():                       # validate everything before any state changes
+                if sid not in self._sessions:
+                    raise KeyError(f"unknown session {sid}")
                 extra = len(s) % C_
                 if extra:
                     s = s[:-extra]
                     hanging[sid] = s[-extra:]
                 else:
                     hanging[sid] = ""
-                n_new = len(s) // C_
-                if not 0 < n_new <= self.pool.cap_frames:
+                if not 0 < len(s) // C_ <= self.pool.cap_frames:
                     raise ValueError(f"session {sid}: strings must hold 1..{self.pool.cap_frames} frames")
-                st.detok_context = (st.detok_context + s)[-max(len(s), self.context_frames):]
                 flat = chars_to_codes(s, 1, self.codebook_size, unicode_offset=self.unicode_offset)[0]
                 new_codes[sid] = np.ascontiguousarray(np.asarray(flat).reshape(-1, C_).T)
+                trimmed[sid] = s
+            for sid, s in trimmed.items():
+                st = self._sessions[sid]
+                st.detok_context = (st.detok_context + s)[-max(len(s), self.context_frames):]
                 wants[sid] = int(len(s) / (self.framerate * C_) * self.sampling_rate) + preroll_samples
                 ctx_frames_before = self.pool.context_len(st.slot)[1]
-                groups.setdefault((ctx_frames_before, n_new, wants[sid]), []).append(sid)
+                groups.setdefault((ctx_frames_before, len(s) // C_, wants[sid]), []).append(sid)
             out = {}
             for (_, _, want), sids in groups.items():
                 slots = [self._sessions[s].slot for s in sids]
@@ -248,7 +253,15 @@ class ThreadedSessionBatcher(SessionBatcher):
                 res = self.tokenize_audio({sid: chunk for sid, chunk, _ in batch})
                 for sid, _, fut in batch:
                     fut.set_result(res[sid])
-            except Exception as ex:                        # noqa: BLE001
+            except (ValueError, KeyError):
+                # a malformed request (bad chunk length, closed session) is rejected BEFORE anything is pushed: serve the
+                # others, fail only the offender
+                for sid, chunk, fut in batch:
+                    try:
+                        fut.set_result(self.tokenize_audio({sid: chunk})[sid])
+                    except Exception as ex:                # noqa: BLE001
+                        fut.set_exception(ex)
+            except Exception as ex:                        # noqa: BLE001  (engine failure: state unknown, everyone hears about it)
                 for _, _, fut in batch:
                     if not fut.done():
                         fut.set_exception(ex)

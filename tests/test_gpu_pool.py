@@ -135,6 +135,40 @@ def test_threaded_batcher_serves_request_threads(gen):
         gen.set_option("small_m_split_k", 1)
 
 
+def test_a_malformed_request_fails_alone(gen):
+    """One bad request in a tick (empty chunk, closed session) must not take the other streams down, and a rejected
+    batch must leave every session's context untouched (validation happens before anything is pushed)."""
+    gen.set_option("small_m_split_k", 0)
+    bat = ThreadedSessionBatcher(gen, max_sessions=4, max_wait_ms=20.0)
+    try:
+        good, bad = bat.open_session(), bat.open_session()
+        ref = pkg.AudioTokenizer(codec_model=gen, device="cuda")
+        res = {}
+
+        def call(name, sid, chunk):
+            try:
+                res[name] = bat.tokenize_audio_one(sid, chunk)
+            except Exception as ex:                                      # noqa: BLE001
+                res[name] = ex
+
+        ts = [threading.Thread(target=call, args=("good", good, _audio(0)[:1600])),
+              threading.Thread(target=call, args=("empty", bad, np.zeros(0, np.float32))),
+              threading.Thread(target=call, args=("closed", 12345, _audio(1)[:1600]))]
+        [t.start() for t in ts]; [t.join() for t in ts]
+        assert isinstance(res["empty"], ValueError) and isinstance(res["closed"], KeyError)
+        assert res["good"] == ref.tokenize_audio(_audio(0)[:1600])
+        # detokenize: the bad string is found before any context changes
+        s = res["good"]
+        with pytest.raises(ValueError):
+            bat.detokenize_audio({good: s, bad: ""})
+        assert bat._sessions[good].detok_context == "" and bat.pool.context_len(bat._sessions[good].slot)[1] == 0
+        out = bat.detokenize_audio({good: s})
+        assert out[good][0][1].shape == (1600,)
+    finally:
+        bat.shutdown()
+        gen.set_option("small_m_split_k", 1)
+
+
 def test_eight_sessions_cost_less_than_two():
     """Default spec: one launch for 8 sessions (800 rows) against one session alone (100 rows)."""
     spec = pkg.DEFAULT_SPEC
