@@ -424,11 +424,26 @@ class DeviceIngest:
             raise RuntimeError("DeviceIngest needs a B200Generator on its CUDA device; there is no host fallback")
         self.gen, self.torch = gen, torch
         self._taps = {}
+        self._host_free = []                 # pinned staging buffers handed back by finished runs (cudaHostAlloc is ~ms per call)
+        self._host_lock = __import__("threading").Lock()
         self.copy_stream = torch.cuda.Stream(device=gen.device)
 
     # ---- buffers
     def host_buffer(self, nbytes: int):
+        """A pinned uint8 tensor of at least nbytes: the smallest recycled one that fits, else a new allocation."""
+        with self._host_lock:
+            fits = [b for b in self._host_free if nbytes <= b.numel() <= max(4 * nbytes, 1 << 20)]
+            if fits:
+                buf = min(fits, key=lambda b: b.numel())
+                self._host_free = [b for b in self._host_free if b is not buf]
+                return buf
         return self.torch.empty(nbytes, dtype=self.torch.uint8).pin_memory()
+
+    def recycle(self, buf) -> None:
+        """Hand a pinned buffer back (staging buffers at the end of a run, code buffers after the write); at most 64 are kept."""
+        with self._host_lock:
+            if buf is not None and len(self._host_free) < 64:
+                self._host_free.append(buf)
 
     def _taps_on_device(self, plan: ResamplePlan):
         key = (plan.up, plan.down)
@@ -487,13 +502,26 @@ class DeviceIngest:
         return self.convert(pcm, self.upload(pcm, host_tensor), mono)
 
     def codes_to_host(self, codes):
-        """Device int64 code tensors -> (pinned host tensors, wait()) — async D2H on the current stream."""
+        """Device int64 code tensors -> (pinned host tensors, wait) — async D2H on the current stream.  wait() blocks until
+        the copies have landed; wait.release() (optional, once the caller is done with the host tensors) hands the
+        pinned memory back for the next file."""
         torch = self.torch
-        host = []
+        host, bufs = [], []
         for c in codes:
-            hc = torch.empty(c.numel(), dtype=torch.int64).pin_memory()
+            raw = self.host_buffer(max(8 * c.numel(), 8))
+            hc = raw[: 8 * c.numel()].view(torch.int64)
             hc.copy_(c, non_blocking=True)
             host.append(hc)
+            bufs.append(raw)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.gen.device))
-        return host, ev.synchronize
+
+        def wait():
+            ev.synchronize()
+
+        def release():
+            for b in bufs:
+                self.recycle(b)
+
+        wait.release = release
+        return host, wait

@@ -94,6 +94,16 @@ class _PinnedPool:
     def release(self, buf: Optional[torch.Tensor]) -> None:
         self.free.put(buf)
 
+    def drain(self) -> List[torch.Tensor]:
+        out = []
+        while True:
+            try:
+                buf = self.free.get_nowait()
+            except queue.Empty:
+                return out
+            if buf is not None:
+                out.append(buf)
+
 
 def encode_corpus(gen, audio_path: str, codes_path: str, codec_model: str = "MagiCodec-50Hz-Base",
                   chunk_size_secs: float = 0.1, context_secs: float = 2.0, batch_size: int = 256, stereo: bool = False,
@@ -137,7 +147,14 @@ def encode_corpus(gen, audio_path: str, codes_path: str, codec_model: str = "Mag
         todo.append((fid, rel, dsts))
 
     # ---- pipeline
-    ingest = ingest if ingest is not None else audio_io.DeviceIngest(gen)
+    if ingest is None:                                               # one per engine: its copy stream, filter taps and pinned staging
+        ingest = getattr(gen, "_corpus_ingest", None)               # buffers outlive a run (a second run in the process reuses them)
+        if ingest is None:
+            ingest = audio_io.DeviceIngest(gen)
+            try:
+                gen._corpus_ingest = ingest
+            except AttributeError:
+                pass
     pool = _PinnedPool(prefetch_files + 1, ingest.host_buffer)
     write_q: "queue.Queue" = queue.Queue(maxsize=4 * (prefetch_files + 1))    # a slow disk throttles the encoder, not memory
     lock = threading.Lock()
@@ -184,6 +201,10 @@ def encode_corpus(gen, audio_path: str, codes_path: str, codec_model: str = "Mag
                     os.replace(tmp, dst)
                 with lock:
                     manifest.extend(entries)
+                release = getattr(wait, "release", None)              # pinned code buffers go back to the ingest's pool
+                if release is not None:
+                    host_codes = None
+                    release()
             except Exception as ex_:                                  # noqa: BLE001
                 for tmp, _ in tmps:
                     try:
@@ -233,6 +254,9 @@ def encode_corpus(gen, audio_path: str, codes_path: str, codec_model: str = "Mag
         ex.shutdown(wait=True, cancel_futures=True)
         write_q.put(None)
         wt.join()
+        if hasattr(ingest, "recycle"):
+            for buf in pool.drain():
+                ingest.recycle(buf)
     if stats is not None:
         stats["encoded_audio_secs"] = stats.get("encoded_audio_secs", 0.0) + encoded_secs
         stats["files_encoded"] = stats.get("files_encoded", 0) + len(todo) - len(errors)
