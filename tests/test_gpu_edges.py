@@ -281,3 +281,31 @@ def test_look_ahead_spec_skips_the_causal_warmup_shortcut():
     # and the shortcut WOULD have been wrong here: the prefix trick changes warm-up codes under look-ahead
     whole = g.encode(streams[0][None, :32000])[0]
     assert not torch.equal(whole[:95], fast[0][:95])
+
+
+@pytest.mark.parametrize("context_secs", [0.3, 2.0, 4.0, 6.5])
+@pytest.mark.parametrize("mode", [0, 2])
+def test_streaming_with_other_context_lengths_equals_hand_built_windows(gen, context_secs, mode):
+    """context_secs is a constructor argument of the reference (audio_tokenizer.py:15; realtime_agent_config.py sets it):
+    0.3 s (15 frames), 2.0 s (one 128-row tile), 4.0 s (200 rows: two tiles, per-layer row compaction inside the few-rows
+    regime) and 6.5 s (325 rows: beyond the few-rows regime).  Every streamed call must equal the stateless engine call on
+    the window the reference would have built, with the session's kernels (mode 2) and the batch-invariant ones (mode 0)."""
+    wav = pkg.synth_audio(16000 * 9, file_id=31).numpy()
+    gen.set_option("small_m_split_k", mode)
+    try:
+        tok = pkg.AudioTokenizer(codec_model=gen, context_secs=context_secs, device="cuda")
+        ctx_samples, ctx_frames = int(context_secs * 16000), int(context_secs * 50)
+        chunk, text = 1600, ""
+        for i in range(int(8.5 * 16000) // chunk):
+            s = tok.tokenize_audio(wav[i * chunk:(i + 1) * chunk])
+            lo = max(0, (i + 1) * chunk - max(ctx_samples, chunk))
+            window = torch.from_numpy(wav[None, lo:(i + 1) * chunk]).cuda()
+            want = gen.encode(window, keep_last_frames=5)[0].cpu().numpy()
+            assert [ord(c) - tok.unicode_offset for c in s] == list(want), f"encode call {i}"
+            text += s
+            (_, w), _, _ = tok.detokenize_audio(s, preroll_samples=320)
+            codes = np.array([ord(c) - tok.unicode_offset for c in text[-max(ctx_frames, 5):]], dtype=np.int64)
+            want_w = gen.decode(torch.from_numpy(codes[None]).cuda(), keep_last_samples=1600 + 320)[0].cpu().numpy()
+            assert np.array_equal(w, want_w), f"decode call {i}"
+    finally:
+        gen.set_option("small_m_split_k", 1)
