@@ -389,7 +389,7 @@ def main():
 
 
 def bench_cli(args, gen, dev, rank, world, dev_files, file_ids, total_audio_secs, sync_all):
-    """`e2e_cli`: audio_to_codes.encode_corpus (the body of `python -m realtime_codec_agent_b200.audio_to_codes`) over this
+    """`e2e_cli`: audio_to_codes.encode_corpus (the body of `python -m rca_b200_loader audio_to_codes`) over this
     run's audio as 16-bit .wav files on tmpfs: header probe + duration-balanced sharding, loader threads reading into
     pinned buffers, H2D of the int16 payload on a copy stream, device ingest kernels, corpus encode, writer thread with
     atomic .npy writes, and the manifest all-gather — wall clock between barriers, max over ranks."""
@@ -427,7 +427,7 @@ def bench_cli(args, gen, dev, rank, world, dev_files, file_ids, total_audio_secs
         total = sum(walls)
         return {"value": total_audio_secs * len(walls) / total, "unit": UNIT, "ms_per_step": 1e3 * total / len(walls),
                 "files": nfiles, "input": "16-bit PCM .wav on tmpfs", "h2d_bytes_per_step": int(sum(d.numel() for d in dev_files) * 2),
-                "api": "audio_to_codes.encode_corpus (what `python -m realtime_codec_agent_b200.audio_to_codes` runs after loading the model)"}
+                "api": "audio_to_codes.encode_corpus (what `python -m rca_b200_loader audio_to_codes` runs after loading the model)"}
     finally:
         sync_all()
         if rank == 0:

@@ -21,3 +21,23 @@ def load():
 
 
 package = load()
+
+
+def _main(argv):
+    """``python -m rca_b200_loader <submodule> [args...]`` runs ``realtime_codec_agent_b200.<submodule>.main(args)`` —
+    the ``python -m package.module`` form for a package whose directory name is not an identifier, e.g.
+    ``torchrun --nproc-per-node 8 -m rca_b200_loader audio_to_codes --audio_path raw --codes_path codes``."""
+    import importlib
+    if not argv or argv[0] in ("-h", "--help"):
+        print(_main.__doc__)
+        return 0 if argv else 2
+    mod = importlib.import_module(f"{PKG_NAME}.{argv[0]}")
+    if not hasattr(mod, "main"):
+        print(f"{PKG_NAME}.{argv[0]} has no main()", file=sys.stderr)
+        return 2
+    mod.main(argv[1:])
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(_main(sys.argv[1:]))

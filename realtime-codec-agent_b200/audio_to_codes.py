@@ -2,7 +2,7 @@
 ``python -m codec_bpe.audio_to_codes`` that /root/reference/encode_audio_gpu_{1..4}.sh:1-8 and
 encode_audio_stereo.sh:1-9 invoke:
 
-    python -m realtime_codec_agent_b200.audio_to_codes --audio_path data/audio/raw \
+    python -m rca_b200_loader audio_to_codes --audio_path data/audio/raw \
         --codes_path data/audio/codes --chunk_size_secs 0.1 --context_secs 2.0 --batch_size 256 \
         --codec_model MagiCodec-50Hz-Base [--stereo] [--audio_filter CallFriend CallHome ...]
 
@@ -265,7 +265,7 @@ def encode_corpus(gen, audio_path: str, codes_path: str, codec_model: str = "Mag
 
 
 def main(argv: Optional[Sequence[str]] = None) -> None:
-    ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
+    ap = argparse.ArgumentParser(prog="python -m rca_b200_loader audio_to_codes", description=__doc__.split("\n\n")[0])
     ap.add_argument("--audio_path", required=True)
     ap.add_argument("--codes_path", required=True)
     ap.add_argument("--chunk_size_secs", type=float, default=0.1)

@@ -1,7 +1,7 @@
 """In-tree build of the C-ABI library (nvcc -> realtime-codec-agent_b200/libmagicodec_b200.so).
 
 sm_100a only: `-gencode arch=compute_100a,code=sm_100a`.  The built .so is git-ignored but travels
-to the GPU box with the repo snapshot.  `python -m realtime_codec_agent_b200.build` or
+to the GPU box with the repo snapshot.  `python -m rca_b200_loader build` or
 `__graft_entry__.build()`.
 """
 from __future__ import annotations
@@ -66,5 +66,10 @@ def build(force: bool = False, verbose: bool = False, trace: bool = False) -> st
     return lib_path
 
 
+def main(argv=None) -> None:
+    argv = sys.argv[1:] if argv is None else argv
+    print(build(force="--force" in argv, verbose="-v" in argv, trace="--trace" in argv))
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))
+    main()

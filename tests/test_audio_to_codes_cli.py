@@ -151,3 +151,16 @@ def test_tokenizer_resamples_with_the_soxr_class_filter():
     x = pkg.synth_audio(24000, file_id=8).numpy()
     got = tok._prep_audio_for_tokenization((24000, x))
     assert got.shape == (16000,) and np.array_equal(got, audio_io.resample(x, 24000, 16000))
+
+
+def test_documented_command_line_resolves():
+    """`python -m rca_b200_loader audio_to_codes ...` (the package directory name is not an identifier,
+    so the repo-root loader module is the `-m` entry; torchrun takes the same `-m`)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "rca_b200_loader", "audio_to_codes", "--help"], cwd=root, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0 and "--audio_path" in r.stdout and "--stereo" in r.stdout
+    r = subprocess.run([sys.executable, "-m", "rca_b200_loader", "no_such_module"], cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0

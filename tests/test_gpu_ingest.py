@@ -126,14 +126,10 @@ def test_cli_under_torchrun_on_two_gpus(tmp_path):
     env = dict(os.environ, MAGICODEC_B200_CHECKPOINT=str(ckpt), PYTHONPATH=ROOT)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         env.pop(k, None)
-    launcher = ("import sys; sys.path.insert(0, %r); import rca_b200_loader; "
-                "from realtime_codec_agent_b200 import audio_to_codes; audio_to_codes.main(sys.argv[1:])" % ROOT)
-    lp = tmp_path / "launch.py"
-    lp.write_text(launcher)
 
     def run(nproc, codes):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
-               "--master-port", "29611", str(lp), "--audio_path", raw, "--codes_path", str(codes), "--batch_size", "16"]
+               "--master-port", "29611", "-m", "rca_b200_loader", "audio_to_codes", "--audio_path", raw, "--codes_path", str(codes), "--batch_size", "16"]
         r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
         out = codes / "MagiCodec-50Hz-Base" / "0.1s_2.0s" / "mono"
