@@ -49,6 +49,11 @@ def load_magicodec_model(name_or_path: str, device: torch.device):
     if path:
         spec, weights = load_checkpoint(path)
     else:
+        import warnings
+        warnings.warn(f"load_magicodec_model({name_or_path!r}): no checkpoint file and $MAGICODEC_B200_CHECKPOINT is not set — "
+                      "using SEEDED RANDOM weights of the default spec (benchmark / test mode; the codes carry no audio meaning). "
+                      "Convert a real checkpoint with weights.save_checkpoint and point $MAGICODEC_B200_CHECKPOINT at it.",
+                      RuntimeWarning, stacklevel=2)
         spec, weights = DEFAULT_SPEC, init_random_weights(DEFAULT_SPEC, seed=0)
     return B200Generator(spec, weights, device=device), None, None
 
