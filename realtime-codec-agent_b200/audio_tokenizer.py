@@ -156,11 +156,33 @@ class AudioTokenizer:
 
     def tokenize_audio(self, audio: AudioLike) -> str:
         with self._lock:
-            return self._tokenize_audio_locked(audio)
+            new = self._prep_audio_for_tokenization(audio)
+            if self._native:
+                text = self._tokenize_on_session(new)
+                if text is not None:
+                    return text
+            return self._tokenize_audio_locked(new)
+
+    def _tokenize_on_session(self, new: np.ndarray) -> Optional[str]:
+        """The steady state of the full-duplex loop (one chunk per call, device-resident context): no torch call, no
+        context manager — every microsecond here is on the per-frame latency (the engine call is ~0.35 ms).  Returns None
+        WITHOUT touching any state when the call has to take the general path."""
+        C = self.num_channels
+        n_new = new.shape[-1]
+        sess = self._stream_session()                                # before the context changes: mirrors it from the start
+        if not (self._session_audio_ok and 0 < n_new <= sess.cap_samples):
+            return None
+        chunk = new.reshape(C, -1)
+        self._append_context(chunk)
+        n_chars = int(n_new / self.sampling_rate * self.framerate * C)
+        frames_needed = -(-n_chars // C) if n_chars > 0 else 0       # 0 -> all frames ([-0:] keeps everything)
+        codes = sess.push_audio(chunk, frames_needed)                # [C, k] int64
+        pts = (codes[0] if C == 1 else np.ascontiguousarray(codes.T).reshape(-1)) + self.unicode_offset
+        text = pts.astype("<u4").tobytes().decode("utf-32-le", errors="surrogatepass")
+        return text[-n_chars:]
 
     @torch.inference_mode()
-    def _tokenize_audio_locked(self, audio: AudioLike) -> str:
-        new = self._prep_audio_for_tokenization(audio)
+    def _tokenize_audio_locked(self, new: np.ndarray) -> str:
         n_new = new.shape[-1]
         C = self.num_channels
         sess = self._stream_session() if self._native else None      # before the context changes: mirrors it from the start
@@ -225,7 +247,29 @@ class AudioTokenizer:
     # ----------------------------------------------------------------- decode
     def detokenize_audio(self, audio_codes_str: str, preroll_samples: int = 0):
         with self._lock:
+            if self._native:
+                fast = self._detokenize_on_session(audio_codes_str, preroll_samples)
+                if fast is not None:
+                    return fast
             return self._detokenize_audio_locked(audio_codes_str, preroll_samples)
+
+    def _detokenize_on_session(self, audio_codes_str: str, preroll_samples: int):
+        """Steady-state twin of _detokenize_audio_locked (same bookkeeping, same results) without a torch call; returns
+        None WITHOUT touching any state when the general path has to run."""
+        C = self.num_channels
+        audio_codes_str, end_hanging = self._drop_hanging_channel_codes(audio_codes_str)
+        sess = self._stream_session()
+        n_chars = len(audio_codes_str)
+        if not (self._session_codes_ok and 0 < n_chars // C <= sess.cap_frames):
+            return None
+        self.detokenize_context = (self.detokenize_context + audio_codes_str)[-max(n_chars, self.context_frames):]
+        want = int(self.get_audio_codes_str_secs(audio_codes_str) * self.sampling_rate) + preroll_samples
+        pts = np.frombuffer(audio_codes_str.encode("utf-32-le", errors="surrogatepass"), dtype="<u4").astype(np.int64)
+        pts -= self.unicode_offset
+        codes = pts[None] if C == 1 else np.ascontiguousarray(pts.reshape(-1, C).T)      # [C, F] (:116)
+        wav = sess.push_codes(codes, want)                           # [C, Tk] float32, a fresh array
+        preroll_left = max(0, preroll_samples - want + wav.shape[-1])
+        return (self.sampling_rate, wav[0] if C == 1 else wav), end_hanging, preroll_left
 
     @torch.inference_mode()
     def _detokenize_audio_locked(self, audio_codes_str: str, preroll_samples: int = 0):

@@ -11,7 +11,6 @@ owns the device buffers and the stream.  Nothing here falls back to PyTorch ops 
 """
 from __future__ import annotations
 
-import contextlib
 import ctypes as C
 import threading
 from typing import Dict, Optional
@@ -167,9 +166,9 @@ class StreamSession:
         n = chunk.shape[1]
         out = np.empty((self.channels, self.cap_frames), dtype=np.int64)
         got = C.c_int32(0)
-        with self.gen._serial():
+        with self.gen._serial() as st:
             rc = self.gen._lib.mc_stream_push_audio(self._h, chunk.ctypes.data, n, keep_frames, out.ctypes.data, C.byref(got),
-                                                    self.gen._stream())
+                                                    st.cuda_stream)
             nat.check(self.gen._lib, self.gen._handle, rc, "mc_stream_push_audio")
         return out.reshape(-1)[: self.channels * got.value].reshape(self.channels, got.value)
 
@@ -180,9 +179,9 @@ class StreamSession:
         n = codes.shape[1]
         out = np.empty((self.channels * self.cap_samples,), dtype=np.float32)
         got = C.c_int32(0)
-        with self.gen._serial():
+        with self.gen._serial() as st:
             rc = self.gen._lib.mc_stream_push_codes(self._h, codes.ctypes.data, n, keep_samples, out.ctypes.data, C.byref(got),
-                                                    self.gen._stream())
+                                                    st.cuda_stream)
             nat.check(self.gen._lib, self.gen._handle, rc, "mc_stream_push_codes")
         return out[: self.channels * got.value].reshape(self.channels, got.value)
 
@@ -203,9 +202,9 @@ class StreamSession:
         codes = np.ascontiguousarray(codes, dtype=np.int64).reshape(-1)
         out = np.empty((self._emit_floats,), dtype=np.float32)
         had = C.c_int32(0)
-        with self.gen._serial():
+        with self.gen._serial() as st:
             rc = self.gen._lib.mc_stream_push_codes_emit(self._h, codes.ctypes.data, codes.shape[0], out.ctypes.data, C.byref(had),
-                                                         self.gen._stream())
+                                                         st.cuda_stream)
             nat.check(self.gen._lib, self.gen._handle, rc, "mc_stream_push_codes_emit")
         return out, bool(had.value)
 
@@ -254,6 +253,35 @@ class _Quantizer:
         return z_q, idx
 
 
+class _Serial:
+    """Context manager behind B200Generator._serial (a plain class: this sits on the per-frame latency path, and a
+    generator-based context manager plus an event record per call cost more than the bookkeeping they do).  The device
+    ordering is established only when the stream CHANGES: the new stream then waits for everything queued on the old one
+    (Stream.wait_stream records the event at that moment, i.e. after the earlier call's kernels)."""
+    __slots__ = ("gen",)
+
+    def __init__(self, gen: "B200Generator"):
+        self.gen = gen
+
+    def __enter__(self):
+        gen = self.gen
+        gen._lock.acquire()
+        try:
+            st = torch.cuda.current_stream(gen.device)
+            last = gen._last_stream
+            if last is not None and last.cuda_stream != st.cuda_stream:
+                st.wait_stream(last)
+            gen._last_stream = st
+            return st
+        except BaseException:
+            gen._lock.release()
+            raise
+
+    def __exit__(self, *exc):
+        self.gen._lock.release()
+        return False
+
+
 class B200Generator:
     is_b200_native = True
 
@@ -300,8 +328,7 @@ class B200Generator:
         # serialised on the host (threads: tts_server.py:158 runs Flask threaded on one tokenizer; two tokenizers on
         # one model: realtime_agent_resources.py:41-49) and ordered on the device across streams.
         self._lock = threading.RLock()
-        self._last_event = torch.cuda.Event()
-        self._last_stream = None
+        self._last_stream = None          # torch stream of the previous engine call (ordering across streams: _Serial)
 
     # ---- nn.Module-ish surface used by AudioTokenizer.__init__ (:28)
     def eval(self):
@@ -324,19 +351,11 @@ class B200Generator:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    @contextlib.contextmanager
-    def _serial(self):
-        """Host lock + device ordering for one engine call: work queued on another stream by the previous call must
-        be finished with the shared workspace before this call's kernels touch it."""
-        with self._lock:
-            st = torch.cuda.current_stream(self.device)
-            if self._last_stream is not None and self._last_stream != st.cuda_stream:
-                st.wait_event(self._last_event)
-            try:
-                yield st
-            finally:
-                self._last_event.record(st)
-                self._last_stream = st.cuda_stream
+    def _serial(self) -> "_Serial":
+        """Host lock + device ordering for one engine call: work queued on ANOTHER stream by an earlier call must be
+        finished with the shared workspace before this call's kernels touch it.  `with gen._serial() as st:` yields the
+        calling thread's current torch stream (st.cuda_stream is what the C ABI takes)."""
+        return _Serial(self)
 
     def frames_for(self, samples: int) -> int:
         return -(-samples // self.hop)
